@@ -1,0 +1,188 @@
+/*
+ * paresis_b200 -- C ABI of the B200 (sm_100a) image-formation library.
+ *
+ * This is the drop-in boundary for PARESIS's per-(energy, membrane position) hot path.
+ * PARESIS has no FFI of its own: the functions below replace, one for one, the Python /
+ * Numba callables its orchestration layer invokes.  Each entry cites
+ * the reference interface it stands in for, as path:line under /root/reference/CodePython.
+ *
+ * Conventions
+ *   - plain C: raw pointers, sizes, scalars by value; no torch / C++ types.
+ *   - every array pointer is DEVICE memory unless the parameter name ends in `_host`.
+ *   - images are row-major [nx][ny] (axis 0 = "x" = row, as in the reference), pitch = ny.
+ *   - the caller owns all memory; the library owns only cuFFT plans (explicit create/destroy).
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream.
+ *   - return value: PARESIS_OK or an error code; paresis_last_error() gives the text.
+ *   - `flag` (nullable) is a device int that kernels OR status bits into
+ *     (PARESIS_FLAG_NONFINITE = the reference's "nans or insane values" guard,
+ *     refractionFileNumba2.py:81-82); the host shim reads it lazily and raises.
+ */
+#ifndef PARESIS_B200_H
+#define PARESIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARESIS_OK 0
+#define PARESIS_ERR_CUDA 1
+#define PARESIS_ERR_ARG 2
+#define PARESIS_ERR_CUFFT 3
+
+#define PARESIS_FLAG_NONFINITE 1
+
+#define PARESIS_MAX_LAYERS 4
+
+typedef void* paresis_stream;
+typedef struct { float re, im; } paresis_c32;
+
+int paresis_version(void);
+const char* paresis_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Refraction model (ray tracing)
+ * ------------------------------------------------------------------------------------- */
+
+/* fastloopNumba(Nx, Ny, I, I2, Dy, Dx, DxFloor, DyFloor) -- refractionFileNumba2.py:198-263
+ * (same body: refractionFileNumba.py:70-135).  out += bilinear scatter of `intensity` by
+ * (dx, dy) pixels.  `margin` is the virtual zero padding of the loop frame: 0 reproduces a
+ * direct call (edge quirk of :238-262 included), 15 / 10 what fastRefraction v2 / v1 see
+ * after pad + crop (refractionFileNumba2.py:65-78).  `variant`: 0 = plain REDs,
+ * 1 = warp-aggregated rows, 2 = warp-aggregated rows + register-carried columns (default). */
+int paresis_splat(const float* intensity, const float* dx, const float* dy, float* out,
+                  int nx, int ny, int margin, int variant, int* flag, paresis_stream stream);
+
+/* fastRefraction(I, phi, z, E, M, pix) -- refractionFileNumba2.py:25-86 (v1:
+ * refractionFileNumba.py:11-68), fused: gradient (np.gradient edge_order=2, :54) ->
+ * displacement in pixels (:55-56) -> clean-up (:59-64) -> scatter (:77) in one kernel.
+ * out[nx][ny] += result.  dx_pad / dy_pad (nullable) receive the cleaned displacement maps
+ * at offset (margin, margin) of a pre-zeroed [(nx+2m)][(ny+2m)] array, which is what the
+ * reference returns (:86).  phi is fp64 so that a phase of ~1e2-1e3 rad keeps its gradient. */
+int paresis_refract_phi(const float* intensity, const double* phi, float* out,
+                        float* dx_pad, float* dy_pad, int nx, int ny, int margin,
+                        double distance_m, double energy_kev, double magnification, double pixel_um,
+                        int* flag, paresis_stream stream);
+
+/* One projected-thickness map and its per-energy coefficients, formed in fp64 on the host:
+ *   grad_obj / grad_ref : pixels of displacement per metre of 2-pixel thickness difference,
+ *                         -delta * z / (h * M) / (2h)    (Sample.py:348 + refractionFileNumba2.py:54-56)
+ *                         for the object beam / the reference beam (0 = map not in that beam)
+ *   atten               : 2 k beta, 1/m (Sample.py:347); applied to the object beam only */
+typedef struct {
+    const float* thickness;
+    float grad_obj;
+    float grad_ref;
+    float atten;
+} paresis_layer;
+
+/* AnalyticalSample.setWaveRT (Sample.py:285-351) + Experiment.refraction (Experiment.py:255-277)
+ * fused for the per-energy loop of computeSampleAndReferenceImages_RT (Experiment.py:463-474):
+ *   I_obj = I_in * exp(-sum atten_m t_m),  D_obj = sum grad_obj_m * d(t_m),  out_obj += scatter
+ *   I_ref = I_in                          D_ref = sum grad_ref_m * d(t_m),  out_ref += scatter
+ * intensity_in may be NULL (uniform `intensity_uniform`, e.g. I0 * flux).  out_ref may be NULL.
+ * Thickness is differenced first and scaled after, so uniform layers cancel exactly. */
+int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
+                           const paresis_layer* layers_host, int n_layers,
+                           float* out_obj, float* out_ref, int nx, int ny, int margin,
+                           int* flag, paresis_stream stream);
+
+/* AnalyticalSample.setWaveRT as a stand-alone call (Sample.py:285-351, no dark-field branch):
+ * I_out = I_in * exp(-sum atten_m t_m); phi_out = phi_in - sum phase_m t_m (phase_m = k delta_m).
+ * phi_in may be NULL (0).  n = pixels. */
+int paresis_transmit_rt(const float* intensity_in, const double* phi_in,
+                        const float* const* thickness_host, const double* atten_host,
+                        const double* phase_host, int n_layers,
+                        float* intensity_out, double* phi_out, size_t n, paresis_stream stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fresnel model
+ * ------------------------------------------------------------------------------------- */
+
+/* AnalyticalSample.setWave (Sample.py:248-282): wave *= exp((-i k delta_m - k beta_m) t_m).
+ * wave_in may be NULL (uniform real amplitude).  atten_m = k beta_m, phase_m = k delta_m. */
+int paresis_transmit_wave(const paresis_c32* wave_in, float amplitude_uniform,
+                          const float* const* thickness_host, const double* atten_host,
+                          const double* phase_host, int n_layers,
+                          paresis_c32* wave_out, size_t n, paresis_stream stream);
+
+typedef struct paresis_fresnel_plan paresis_fresnel_plan;
+
+/* Experiment.wavePropagation (Experiment.py:219-252): reflect-pad by `margin`, FFT,
+ * multiply by the separable transfer function, inverse FFT, crop.  The plan owns the cuFFT
+ * C2C plan of size (nx+2m) x (ny+2m) and the padded work buffer. */
+int paresis_fresnel_plan_create(int nx, int ny, int margin, paresis_fresnel_plan** plan);
+int paresis_fresnel_plan_destroy(paresis_fresnel_plan* plan);
+size_t paresis_fresnel_plan_bytes(const paresis_fresnel_plan* plan);
+
+/* hx[nx+2m], hy[ny+2m]: per-axis transfer vectors in FFT (unshifted) order, prepared in fp64
+ * on the host: hx[i]*hy[j] = exp(-i z (u_i^2+v_j^2)/(2kM)) / ((nx+2m)(ny+2m))
+ * (Experiment.py:243-250; the frequency step uses the UNPADDED size, :246-247).
+ * `phase` multiplies the result (the global exp(ikz/M) of :250, or 1).
+ * If intensity_acc != NULL the kernel adds |wave|^2 into it (Experiment.py:351-358) and
+ * wave_out may be NULL. */
+int paresis_fresnel_propagate(paresis_fresnel_plan* plan, const paresis_c32* wave_in,
+                              const paresis_c32* hx, const paresis_c32* hy, paresis_c32 phase,
+                              paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Detector
+ * ------------------------------------------------------------------------------------- */
+
+/* Detector.detection up to (not including) the Poisson draw -- Detector.py:92-110 and the
+ * crop of :118: reflect-pad 15*os, source blur (fftconvolve 'same' with
+ * create_gaussian_shape(sigma), :96-99), resize = os x os SUM binning (:103, :185-198),
+ * PSF blur (:106-108).  Kernels are the separable 1-D factors of create_gaussian_shape
+ * (Detector.py:201-220), length 2*half+1, built on the host; half = 0 skips that blur.
+ * `work` must hold paresis_detect_work_floats(...) floats.  expect_out[det_x][det_y]. */
+size_t paresis_detect_work_floats(int nx, int ny, int oversampling, int det_x, int det_y);
+int paresis_detect(const float* image, int nx, int ny, int oversampling, int det_x, int det_y,
+                   const float* src_kernel, int src_half, const float* psf_kernel, int psf_half,
+                   float* work, float* expect_out, paresis_stream stream);
+
+/* rs.poisson(detectedImage) -- Detector.py:113-115.  Counter-based Philox4x32-10: the draw
+ * for pixel p depends only on (seed, sequence, p), so results do not depend on launch shape
+ * or on how positions are sharded over GPUs. */
+int paresis_poisson(const float* expect, float* counts, size_t n, uint64_t seed, uint64_t sequence,
+                    paresis_stream stream);
+
+/* resize(img, sizeX, sizeY) stand-alone -- Detector.py:185-198. */
+int paresis_bin_sum(const float* image, int nx, int ny, int size_x, int size_y, float* out,
+                    paresis_stream stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Geometry (projected thickness maps)
+ * ------------------------------------------------------------------------------------- */
+
+/* getMembraneSegmentedFromFile -- Samples/getMembraneFromFile.py:127-161,168: rasterise
+ * spherical caps, all layers.  spheres[n][3] = (c0, c1, radius) in micrometres, already
+ * rescaled / shifted / tiled (:95-124, done on the host).  offsets_host[layer][2] = the two
+ * np.random.randint draws per layer (:139-140), x first.  thickness_out[dim_x][dim_y] is
+ * overwritten, in metres. */
+int paresis_raster_spheres(const double* spheres, int n_spheres, double pix_um,
+                           const int64_t* offsets_host, int n_layers, int dim_x, int dim_y,
+                           int margin, float* thickness_out, paresis_stream stream);
+
+/* CreateSampleSphere -- Samples/createSampGeom.py:41-53. */
+int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, float* out,
+                       paresis_stream stream);
+
+/* CreateSampleCylindre -- Samples/createSampGeom.py:87-106, including the cv2.warpAffine
+ * (imutils.rotate) fixed-point sampling of the rotated 2N x 2N canvas. */
+int paresis_cylinder_map(double radius_um, double angle_deg, int dim_x, int dim_y, double pix_um,
+                         float* out, paresis_stream stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Small utilities used by the host shim
+ * ------------------------------------------------------------------------------------- */
+int paresis_fill(float* dst, float value, size_t n, paresis_stream stream);
+int paresis_axpy(float* dst, const float* src, float scale, size_t n, paresis_stream stream); /* dst += scale*src */
+/* mean of an image (np.mean at Experiment.py:485-486), result to a device double */
+int paresis_mean(const float* src, size_t n, double* out, paresis_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARESIS_B200_H */

@@ -1,0 +1,267 @@
+"""ctypes binding of ``libparesis_b200.so`` (the C ABI declared in ``include/paresis_b200.h``).
+
+There is no fallback: if the library is missing or does not load, importing this module
+raises.  PyTorch is used only for device memory and streams; tensors cross the boundary as
+raw ``data_ptr()`` values.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libparesis_b200.so")
+
+OK = 0
+FLAG_NONFINITE = 1
+MAX_LAYERS = 4
+REFRACTION_MARGIN = 15   # refractionFileNumba2.py:50
+REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
+
+EXPORTS = (
+    "paresis_version", "paresis_last_error", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
+    "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
+    "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_detect_work_floats", "paresis_detect",
+    "paresis_poisson", "paresis_bin_sum", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
+    "paresis_fill", "paresis_axpy", "paresis_mean",
+)
+
+
+class ParesisError(RuntimeError):
+    pass
+
+
+class Layer(ctypes.Structure):
+    _fields_ = [("thickness", ctypes.c_void_p), ("grad_obj", ctypes.c_float), ("grad_ref", ctypes.c_float),
+                ("atten", ctypes.c_float)]
+
+
+class C32(ctypes.Structure):
+    _fields_ = [("re", ctypes.c_float), ("im", ctypes.c_float)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "paresis_b200: %s not found. Build it with `python -m paresis_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    missing = [n for n in EXPORTS if not hasattr(lib, n)]
+    if missing:
+        raise ImportError("paresis_b200: %s lacks symbols %s" % (LIB_PATH, missing))
+    vp, ci, cd, cf, sz, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
+    lib.paresis_version.restype = ci
+    lib.paresis_last_error.restype = ctypes.c_char_p
+    sig = {
+        "paresis_splat": [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp],
+        "paresis_refract_phi": [vp, vp, vp, vp, vp, ci, ci, ci, cd, cd, cd, cd, vp, vp],
+        "paresis_refract_layers": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, ci, ci, ci, vp, vp],
+        "paresis_transmit_rt": [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(cd), ctypes.POINTER(cd), ci, vp, vp, sz, vp],
+        "paresis_transmit_wave": [vp, cf, ctypes.POINTER(vp), ctypes.POINTER(cd), ctypes.POINTER(cd), ci, vp, sz, vp],
+        "paresis_fresnel_plan_create": [ci, ci, ci, ctypes.POINTER(vp)],
+        "paresis_fresnel_plan_destroy": [vp],
+        "paresis_fresnel_propagate": [vp, vp, vp, vp, C32, vp, vp, vp],
+        "paresis_detect": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, vp],
+        "paresis_poisson": [vp, vp, sz, u64, u64, vp],
+        "paresis_bin_sum": [vp, ci, ci, ci, ci, vp, vp],
+        "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp],
+        "paresis_sphere_map": [cd, ci, ci, cd, vp, vp],
+        "paresis_cylinder_map": [cd, cd, ci, ci, cd, vp, vp],
+        "paresis_fill": [vp, cf, sz, vp],
+        "paresis_axpy": [vp, vp, cf, sz, vp],
+        "paresis_mean": [vp, sz, vp, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ci
+    lib.paresis_detect_work_floats.argtypes = [ci, ci, ci, ci, ci]
+    lib.paresis_detect_work_floats.restype = sz
+    lib.paresis_fresnel_plan_bytes.argtypes = [vp]
+    lib.paresis_fresnel_plan_bytes.restype = sz
+    return lib
+
+
+lib = _load()
+
+# Every call below is one (or a few) of OUR kernels; the bench reports this counter.
+launches = 0
+
+
+def _check(rc, what):
+    if rc != OK:
+        raise ParesisError("%s failed (%d): %s" % (what, rc, lib.paresis_last_error().decode()))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ParesisError("expected a contiguous CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise ParesisError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _count(n=1):
+    global launches
+    launches += n
+
+
+def splat(intensity, dx, dy, out, margin=0, variant=2, flag=None):
+    nx, ny = intensity.shape
+    _check(lib.paresis_splat(_ptr(intensity, torch.float32), _ptr(dx, torch.float32), _ptr(dy, torch.float32),
+                             _ptr(out, torch.float32), nx, ny, margin, variant, _ptr(flag, torch.int32), _stream()),
+           "paresis_splat")
+    _count()
+
+
+def refract_phi(intensity, phi, out, distance, energy_kev, magnification, pixel_um, margin=REFRACTION_MARGIN,
+                dx_pad=None, dy_pad=None, flag=None):
+    nx, ny = intensity.shape
+    _check(lib.paresis_refract_phi(_ptr(intensity, torch.float32), _ptr(phi, torch.float64), _ptr(out, torch.float32),
+                                   _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
+                                   float(distance), float(energy_kev), float(magnification), float(pixel_um),
+                                   _ptr(flag, torch.int32), _stream()), "paresis_refract_phi")
+    _count()
+
+
+def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None):
+    """layers: list of (thickness tensor, grad_obj, grad_ref, atten)."""
+    n = len(layers)
+    arr = (Layer * n)()
+    for k, (t, go, gr, at) in enumerate(layers):
+        arr[k].thickness = t.data_ptr()
+        arr[k].grad_obj, arr[k].grad_ref, arr[k].atten = float(go), float(gr), float(at)
+        _ptr(t, torch.float32)
+    nx, ny = out_obj.shape
+    _check(lib.paresis_refract_layers(_ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n,
+                                      _ptr(out_obj, torch.float32), _ptr(out_ref, torch.float32), nx, ny, margin,
+                                      _ptr(flag, torch.int32), _stream()), "paresis_refract_layers")
+    _count()
+
+
+def _layer_arrays(thickness, atten, phase):
+    n = len(thickness)
+    tp = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in thickness])
+    for t in thickness:
+        _ptr(t, torch.float32)
+    at = (ctypes.c_double * max(n, 1))(*[float(a) for a in atten])
+    ph = (ctypes.c_double * max(n, 1))(*[float(p) for p in phase])
+    return n, tp, at, ph
+
+
+def transmit_rt(intensity_in, phi_in, thickness, atten, phase, intensity_out, phi_out):
+    n, tp, at, ph = _layer_arrays(thickness, atten, phase)
+    count = (intensity_out if intensity_out is not None else phi_out).numel()
+    _check(lib.paresis_transmit_rt(_ptr(intensity_in, torch.float32), _ptr(phi_in, torch.float64), tp, at, ph, n,
+                                   _ptr(intensity_out, torch.float32), _ptr(phi_out, torch.float64), count, _stream()),
+           "paresis_transmit_rt")
+    _count()
+
+
+def transmit_wave(wave_in, amplitude_uniform, thickness, atten, phase, wave_out):
+    n, tp, at, ph = _layer_arrays(thickness, atten, phase)
+    _check(lib.paresis_transmit_wave(_ptr(wave_in, torch.complex64), float(amplitude_uniform), tp, at, ph, n,
+                                     _ptr(wave_out, torch.complex64), wave_out.numel(), _stream()),
+           "paresis_transmit_wave")
+    _count()
+
+
+class FresnelPlan:
+    def __init__(self, nx, ny, margin=15):
+        h = ctypes.c_void_p()
+        _check(lib.paresis_fresnel_plan_create(nx, ny, margin, ctypes.byref(h)), "paresis_fresnel_plan_create")
+        self._h = h
+        self.nx, self.ny, self.margin = nx, ny, margin
+
+    def bytes(self):
+        return lib.paresis_fresnel_plan_bytes(self._h)
+
+    def propagate(self, wave_in, hx, hy, phase=1.0 + 0.0j, wave_out=None, intensity_acc=None):
+        ph = C32(float(np.real(phase)), float(np.imag(phase)))
+        _check(lib.paresis_fresnel_propagate(self._h, _ptr(wave_in, torch.complex64), _ptr(hx, torch.complex64),
+                                             _ptr(hy, torch.complex64), ph, _ptr(wave_out, torch.complex64),
+                                             _ptr(intensity_acc, torch.float32), _stream()),
+               "paresis_fresnel_propagate")
+        _count(5)
+
+    def close(self):
+        if self._h:
+            lib.paresis_fresnel_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def detect_work_floats(nx, ny, oversampling, det_x, det_y):
+    return lib.paresis_detect_work_floats(nx, ny, oversampling, det_x, det_y)
+
+
+def detect(image, oversampling, det_x, det_y, src_kernel, psf_kernel, work, expect_out):
+    nx, ny = image.shape
+    sh = 0 if src_kernel is None else (src_kernel.numel() - 1) // 2
+    ph = 0 if psf_kernel is None else (psf_kernel.numel() - 1) // 2
+    _check(lib.paresis_detect(_ptr(image, torch.float32), nx, ny, oversampling, det_x, det_y,
+                              _ptr(src_kernel, torch.float32), sh, _ptr(psf_kernel, torch.float32), ph,
+                              _ptr(work, torch.float32), _ptr(expect_out, torch.float32), _stream()), "paresis_detect")
+    _count(4 if ph else 3)
+
+
+def poisson(expect, counts, seed, sequence):
+    _check(lib.paresis_poisson(_ptr(expect, torch.float32), _ptr(counts, torch.float32), expect.numel(),
+                               int(seed) & (2 ** 64 - 1), int(sequence) & (2 ** 64 - 1), _stream()), "paresis_poisson")
+    _count()
+
+
+def bin_sum(image, size_x, size_y, out):
+    nx, ny = image.shape
+    _check(lib.paresis_bin_sum(_ptr(image, torch.float32), nx, ny, size_x, size_y, _ptr(out, torch.float32), _stream()),
+           "paresis_bin_sum")
+    _count()
+
+
+def raster_spheres(spheres, pix_um, offsets, dim_x, dim_y, margin, out):
+    offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(-1, 2))
+    _check(lib.paresis_raster_spheres(_ptr(spheres, torch.float64), spheres.shape[0], float(pix_um),
+                                      offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), offs.shape[0],
+                                      dim_x, dim_y, margin, _ptr(out, torch.float32), _stream()),
+           "paresis_raster_spheres")
+    _count()
+
+
+def sphere_map(radius_um, dim_x, dim_y, pix_um, out):
+    _check(lib.paresis_sphere_map(float(radius_um), dim_x, dim_y, float(pix_um), _ptr(out, torch.float32), _stream()),
+           "paresis_sphere_map")
+    _count()
+
+
+def cylinder_map(radius_um, angle_deg, dim_x, dim_y, pix_um, out):
+    _check(lib.paresis_cylinder_map(float(radius_um), float(angle_deg), dim_x, dim_y, float(pix_um),
+                                    _ptr(out, torch.float32), _stream()), "paresis_cylinder_map")
+    _count()
+
+
+def fill(dst, value):
+    _check(lib.paresis_fill(_ptr(dst, torch.float32), float(value), dst.numel(), _stream()), "paresis_fill")
+    _count()
+
+
+def axpy(dst, src, scale=1.0):
+    _check(lib.paresis_axpy(_ptr(dst, torch.float32), _ptr(src, torch.float32), float(scale), dst.numel(), _stream()),
+           "paresis_axpy")
+    _count()
+
+
+def mean(src, out):
+    _check(lib.paresis_mean(_ptr(src, torch.float32), src.numel(), _ptr(out, torch.float64), _stream()), "paresis_mean")
+    _count()

@@ -1,0 +1,288 @@
+// Ray-tracing refraction model: the bilinear splat and its fused producers.
+//
+// Reference: refractionFileNumba2.py:25-86 (fastRefraction), :198-263 (fastloopNumba),
+// Sample.py:285-351 (setWaveRT), Experiment.py:463-474 (the per-energy hop sequence).
+//
+// Launch shape (all kernels here): a block is 8 warps side by side, each warp owns a strip of
+// 32 consecutive source columns and walks `rows` consecutive source rows, one row per step.
+// Loads are unit-stride 128 B per warp and issued one row ahead; deposits leave as REDG.ADD.F32
+// after the warp/register aggregation described in splat.cuh.  HBM-bound integer/fp32 work:
+// no tensor cores (there is no contraction on this path).
+#include <math.h>
+
+#include "splat.cuh"
+
+namespace paresis {
+
+constexpr int BLOCK_WARPS = 8;
+constexpr int BLOCK_THREADS = 32 * BLOCK_WARPS;
+
+// ---------------------------------------------------------------------------------------------
+// fastloopNumba: scatter given I, Dx, Dy
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+splat_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const float* __restrict__ Dy,
+             float* __restrict__ out, Frame f, int rows, int* flag) {
+    const int j = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    const int i0 = blockIdx.y * rows;
+    const int i1 = min(i0 + rows, f.nx);
+    const bool live = j < f.ny;
+    Splatter<MODE> sp;
+    sp.init(out, f.ny, flag);
+    constexpr int U = 4;
+    for (int ib = i0; ib < i1; ib += U) {
+        float v[U], dx[U], dy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = ib + u;
+            const bool on = live && i < i1;
+            const size_t p = (size_t)i * f.ny + j;
+            v[u] = on ? ld_stream(I + p) : 0.f;
+            dx[u] = on ? ld_stream(Dx + p) : 0.f;
+            dy[u] = on ? ld_stream(Dy + p) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = ib + u;
+            if (i < i1) {  // warp-uniform
+                Ray q = live ? make_ray(i, j, v[u], dx[u], dy[u], f) : empty_ray();
+                sp.put(q);
+            }
+        }
+    }
+    sp.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused: thickness (or phase) maps -> transmission -> gradient -> displacement -> scatter
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct RefractArgs {
+    const T* map[PARESIS_MAX_LAYERS];
+    float g_obj[PARESIS_MAX_LAYERS];
+    float g_ref[PARESIS_MAX_LAYERS];
+    float att[PARESIS_MAX_LAYERS];
+    const float* I_in;
+    float I_uniform;
+    float* out_obj;
+    float* out_ref;
+    float* dx_pad;   // optional: cleaned object-beam displacement, stored at (+margin, +margin)
+    float* dy_pad;
+    Frame f;
+    int rows;
+    int* flag;
+};
+
+// refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
+__device__ __forceinline__ void clean(float& v, float& dx, float& dy, int nx, int ny) {
+    if (fabsf(dx) < 1e-12f) dx = 0.f;
+    if (fabsf(dy) < 1e-12f) dy = 0.f;
+    const bool bx = fabsf(dx) > (float)nx, by = fabsf(dy) > (float)ny;
+    if (bx | by) v = 0.f;
+    if (bx) dx = 0.f;
+    if (by) dy = 0.f;
+}
+
+template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT, bool WRITE_D>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+refract_kernel(const RefractArgs<T> a) {
+    const Frame f = a.f;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    const int i0 = blockIdx.y * a.rows;
+    const int i1 = min(i0 + a.rows, f.nx);
+    const bool live = j < f.ny;
+    const int jc = live ? j : f.ny - 1;  // dead lanes read a valid address, contribute nothing
+
+    // rolling rows: up = row i-1, mid = row i, dn = row i+1 (difference first, scale after)
+    T up[NM], mid[NM], dn[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        const T* t = a.map[m];
+        mid[m] = ld_stream(t + (size_t)i0 * f.ny + jc);
+        up[m] = i0 > 0 ? ld_stream(t + (size_t)(i0 - 1) * f.ny + jc) : mid[m];
+        dn[m] = i0 + 1 < f.nx ? ld_stream(t + (size_t)(i0 + 1) * f.ny + jc) : mid[m];
+    }
+    float vin = HAS_I ? ld_stream(a.I_in + (size_t)i0 * f.ny + jc) : a.I_uniform;
+
+    Splatter<2> sp_obj, sp_ref;
+    sp_obj.init(a.out_obj, f.ny, a.flag);
+    if (DUAL) sp_ref.init(a.out_ref, f.ny, a.flag);
+
+    for (int i = i0; i < i1; ++i) {
+        // prefetch the row after next and the next intensity before touching this row
+        T nxt[NM];
+        const bool more = i + 2 < f.nx && i + 1 < i1;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) nxt[m] = more ? ld_stream(a.map[m] + (size_t)(i + 2) * f.ny + jc) : dn[m];
+        float vnext = vin;
+        if (HAS_I && i + 1 < i1) vnext = ld_stream(a.I_in + (size_t)(i + 1) * f.ny + jc);
+
+        float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const T* t = a.map[m];
+            // neighbours along the row come from the adjacent lanes; the strip edges load them
+            T lf = __shfl_up_sync(FULL_MASK, mid[m], 1);
+            T rt = __shfl_down_sync(FULL_MASK, mid[m], 1);
+            if (lane == 0 && jc > 0) lf = ld_stream(t + (size_t)i * f.ny + jc - 1);
+            if (lane == 31 && jc + 1 < f.ny) rt = ld_stream(t + (size_t)i * f.ny + jc + 1);
+            // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
+            T gy, gx;
+            if (jc == 0) gy = -(T)3 * mid[m] + (T)4 * rt - ld_stream(t + (size_t)i * f.ny + 2);
+            else if (jc == f.ny - 1) gy = (T)3 * mid[m] - (T)4 * lf + ld_stream(t + (size_t)i * f.ny + f.ny - 3);
+            else gy = rt - lf;
+            if (i == 0) gx = -(T)3 * mid[m] + (T)4 * dn[m] - ld_stream(t + (size_t)2 * f.ny + jc);
+            else if (i == f.nx - 1) gx = (T)3 * mid[m] - (T)4 * up[m] + ld_stream(t + (size_t)(f.nx - 3) * f.ny + jc);
+            else gx = dn[m] - up[m];
+            const float gxf = (float)gx, gyf = (float)gy;
+            dxo = fmaf(a.g_obj[m], gxf, dxo);
+            dyo = fmaf(a.g_obj[m], gyf, dyo);
+            if (DUAL) {
+                dxr = fmaf(a.g_ref[m], gxf, dxr);
+                dyr = fmaf(a.g_ref[m], gyf, dyr);
+            }
+            if (ATT) arg = fmaf(a.att[m], (float)mid[m], arg);
+        }
+        float vo = ATT ? vin * expf(-arg) : vin;   // Sample.py:347
+        float vr = vin;
+        clean(vo, dxo, dyo, f.nx, f.ny);
+        if (DUAL) clean(vr, dxr, dyr, f.nx, f.ny);
+        if (WRITE_D && live) {
+            const size_t pp = (size_t)(i + f.margin) * (f.ny + 2 * f.margin) + (j + f.margin);
+            a.dx_pad[pp] = dxo;
+            a.dy_pad[pp] = dyo;
+        }
+        sp_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
+        if (DUAL) sp_ref.put(live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray());
+
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { up[m] = mid[m]; mid[m] = dn[m]; dn[m] = nxt[m]; }
+        vin = vnext;
+    }
+    sp_obj.finish();
+    if (DUAL) sp_ref.finish();
+}
+
+// rows per warp: enough blocks for ~2 waves of 148 SMs x 8 resident blocks, few halo re-reads
+static int pick_rows(int nx, int ny) {
+    const int strips = div_up(ny, BLOCK_THREADS);
+    const long target_blocks = 148L * 8 * 2;
+    int rows = (int)((long)nx * strips / target_blocks);
+    if (rows < 8) rows = 8;
+    if (rows > 64) rows = 64;
+    return rows;
+}
+
+static int check_frame(int nx, int ny, int margin) {
+    if (nx < 3 || ny < 3 || margin < 0 || (long)nx * ny >= (1L << 30)) {
+        set_last_error("bad frame %d x %d (margin %d): need 3 <= n and nx*ny < 2^30", nx, ny, margin);
+        return PARESIS_ERR_ARG;
+    }
+    return PARESIS_OK;
+}
+
+template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT>
+static int launch_refract(const RefractArgs<T>& a, bool write_d, cudaStream_t s) {
+    dim3 grid(div_up(a.f.ny, BLOCK_THREADS), div_up(a.f.nx, a.rows));
+    if (write_d) refract_kernel<T, NM, DUAL, HAS_I, ATT, true><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    else refract_kernel<T, NM, DUAL, HAS_I, ATT, false><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    PARESIS_LAUNCH_CHECK("refract_kernel");
+    return PARESIS_OK;
+}
+
+template <int NM>
+static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
+    const bool dual = a.out_ref != nullptr, has_i = a.I_in != nullptr;
+    if (dual) return has_i ? launch_refract<float, NM, true, true, true>(a, false, s)
+                           : launch_refract<float, NM, true, false, true>(a, false, s);
+    return has_i ? launch_refract<float, NM, false, true, true>(a, false, s)
+                 : launch_refract<float, NM, false, false, true>(a, false, s);
+}
+
+}  // namespace paresis
+
+using namespace paresis;
+
+extern "C" int paresis_splat(const float* intensity, const float* dx, const float* dy, float* out,
+                             int nx, int ny, int margin, int variant, int* flag, paresis_stream stream) {
+    if (!intensity || !dx || !dy || !out) { set_last_error("paresis_splat: null pointer"); return PARESIS_ERR_ARG; }
+    if (nx < 1 || ny < 1 || margin < 0 || (long)nx * ny >= (1L << 30)) {
+        set_last_error("paresis_splat: bad frame %d x %d margin %d", nx, ny, margin);
+        return PARESIS_ERR_ARG;
+    }
+    Frame f{nx, ny, margin};
+    const int rows = pick_rows(nx, ny);
+    dim3 grid(div_up(ny, BLOCK_THREADS), div_up(nx, rows));
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case 0: splat_kernel<0><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
+        case 1: splat_kernel<1><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
+        case 2: splat_kernel<2><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
+        default: set_last_error("paresis_splat: unknown variant %d", variant); return PARESIS_ERR_ARG;
+    }
+    PARESIS_LAUNCH_CHECK("splat_kernel");
+    return PARESIS_OK;
+}
+
+extern "C" int paresis_refract_phi(const float* intensity, const double* phi, float* out,
+                                   float* dx_pad, float* dy_pad, int nx, int ny, int margin,
+                                   double distance_m, double energy_kev, double magnification, double pixel_um,
+                                   int* flag, paresis_stream stream) {
+    if (!intensity || !phi || !out || ((dx_pad == nullptr) != (dy_pad == nullptr))) {
+        set_last_error("paresis_refract_phi: null pointer");
+        return PARESIS_ERR_ARG;
+    }
+    int rc = check_frame(nx, ny, margin);
+    if (rc) return rc;
+    // refractionFileNumba2.py:47-48, :55-56 -- D = dphi * z / k / (h * M), dphi = numerator / (2h)
+    const double lambda = 6.626 * 1e-34 * 2.998e8 / (energy_kev * 1000 * 1.6e-19);
+    const double k = 2 * M_PI / lambda;
+    const double h = pixel_um * 1e-6;
+    RefractArgs<double> a{};
+    a.map[0] = phi;
+    a.g_obj[0] = (float)(distance_m / k / (h * magnification) / (2.0 * h));
+    a.I_in = intensity;
+    a.out_obj = out;
+    a.dx_pad = dx_pad;
+    a.dy_pad = dy_pad;
+    a.f = Frame{nx, ny, margin};
+    a.rows = pick_rows(nx, ny);
+    a.flag = flag;
+    return launch_refract<double, 1, false, true, false>(a, dx_pad != nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
+                                      const paresis_layer* layers_host, int n_layers,
+                                      float* out_obj, float* out_ref, int nx, int ny, int margin,
+                                      int* flag, paresis_stream stream) {
+    if (!layers_host || !out_obj || n_layers < 1 || n_layers > PARESIS_MAX_LAYERS) {
+        set_last_error("paresis_refract_layers: need 1..%d layers and an output", PARESIS_MAX_LAYERS);
+        return PARESIS_ERR_ARG;
+    }
+    int rc = check_frame(nx, ny, margin);
+    if (rc) return rc;
+    RefractArgs<float> a{};
+    for (int m = 0; m < n_layers; ++m) {
+        if (!layers_host[m].thickness) { set_last_error("paresis_refract_layers: null map %d", m); return PARESIS_ERR_ARG; }
+        a.map[m] = layers_host[m].thickness;
+        a.g_obj[m] = layers_host[m].grad_obj;
+        a.g_ref[m] = layers_host[m].grad_ref;
+        a.att[m] = layers_host[m].atten;
+    }
+    a.I_in = intensity_in;
+    a.I_uniform = intensity_uniform;
+    a.out_obj = out_obj;
+    a.out_ref = out_ref;
+    a.f = Frame{nx, ny, margin};
+    a.rows = pick_rows(nx, ny);
+    a.flag = flag;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (n_layers) {
+        case 1: return dispatch_layers<1>(a, s);
+        case 2: return dispatch_layers<2>(a, s);
+        case 3: return dispatch_layers<3>(a, s);
+        default: return dispatch_layers<4>(a, s);
+    }
+}

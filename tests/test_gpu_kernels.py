@@ -1,0 +1,289 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (paresis_b200._cabi).
+
+Oracle = oracle/paresis_oracle.py (fp64 CPU restatement, pinned to the reference by
+tests/test_oracle_golden.py) and the committed reference goldens themselves.  Tolerance: the
+north-star bound, 1e-5 relative L2 for noise-free fp32 results; bit-level properties (known
+answers, conservation) are checked where the domain offers them.
+"""
+import numpy as np
+import pytest
+
+import paresis_oracle as po
+from conftest import rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def abi():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from paresis_b200 import _cabi
+    return _cabi
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype).contiguous()
+
+
+def run_splat(abi, I, Dx, Dy, margin, variant):
+    out = torch.zeros(I.shape, device="cuda", dtype=torch.float32)
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    abi.splat(dev(I), dev(Dx), dev(Dy), out, margin=margin, variant=variant, flag=flag)
+    return out.cpu().numpy().astype(np.float64), int(flag.item())
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_splat_known_answers(abi, golden, variant):
+    g = golden("splat_kernel")
+    for row in g["known_answers"]:
+        dxv, dyv, want = row[0], row[1], row[2:].reshape(9, 9)
+        I = np.zeros((9, 9)); I[4, 4] = 1.0
+        Dx = np.zeros((9, 9)); Dx[4, 4] = dxv
+        Dy = np.zeros((9, 9)); Dy[4, 4] = dyv
+        got, flag = run_splat(abi, I, Dx, Dy, 0, variant)
+        assert flag == 0
+        assert np.allclose(got, want, rtol=0, atol=1e-7), (dxv, dyv)
+    I = np.zeros((5, 5)); I[4, 2] = 1.0
+    Dx = np.zeros((5, 5)); Dy = np.zeros((5, 5)); Dy[4, 2] = 0.5
+    got, _ = run_splat(abi, I, Dx, Dy, 0, variant)
+    assert np.array_equal(got, g["edge_quirk"])  # the reference's edge quirk, bit for bit
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_splat_reference_frames(abi, golden, variant, tag):
+    g = golden("splat_kernel")
+    got, flag = run_splat(abi, g["I_" + tag], g["Dx_" + tag], g["Dy_" + tag], 0, variant)
+    assert flag == 0
+    assert rel_l2(got, g["out_" + tag]) < 2e-6  # inputs are fp64 goldens rounded to fp32 (|D| up to ~100 px)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape,amp,margin", [((257, 300), 0.7, 15), ((64, 1030), 9.0, 15), ((513, 96), 30.0, 0),
+                                               ((40, 33), 100.0, 10), ((3, 3), 1.0, 0), ((1, 70), 2.0, 0)])
+def test_splat_vs_oracle(abi, variant, shape, amp, margin):
+    rng = np.random.default_rng(hash((shape, margin)) % 1000)
+    x = np.linspace(0, 6, shape[0])[:, None]
+    y = np.linspace(0, 6, shape[1])[None, :]
+    Dx = (amp * np.sin(1.3 * x + 0.4 * y) * np.cos(0.9 * y)).astype(np.float32).astype(np.float64)
+    Dy = (amp * np.cos(0.7 * x) * np.sin(1.1 * y + 0.3 * x)).astype(np.float32).astype(np.float64)
+    Dx[rng.random(shape) < 0.1] = 0.0
+    Dy[rng.random(shape) < 0.1] = 0.0
+    jump = rng.random(shape) < 0.05                      # rays that tear away from their neighbours
+    Dx[jump] += np.float32(5.0) * rng.standard_normal(jump.sum()).astype(np.float32)
+    I = rng.uniform(0.5, 2.0, shape).astype(np.float32).astype(np.float64)
+    want = po.splat(I, Dx, Dy, margin)
+    got, flag = run_splat(abi, I, Dx, Dy, margin, variant)
+    assert flag == 0
+    assert rel_l2(got, want) < 5e-7
+    if margin == 0 and amp < 1:
+        pass
+    # conservation: what stays inside the frame is what the oracle says stays
+    assert abs(got.sum() / want.sum() - 1) < 1e-6
+
+
+def test_splat_flags_nonfinite(abi):
+    I = np.ones((16, 40)); I[3, 3] = np.nan
+    _, flag = run_splat(abi, I, np.zeros((16, 40)), np.zeros((16, 40)), 15, 2)
+    assert flag & abi.FLAG_NONFINITE
+
+
+def test_splat_large_conservation(abi):
+    """Full-size property test (2048^2): rays that stay in the frame conserve the total."""
+    n = 2048
+    x = torch.linspace(0, 40, n, device="cuda")
+    Dx = (3.0 * torch.sin(x)[:, None] * torch.cos(0.5 * x)[None, :]).contiguous()
+    Dy = (2.0 * torch.cos(0.7 * x)[:, None] * torch.sin(x)[None, :]).contiguous()
+    I = torch.ones((n, n), device="cuda")
+    I[:8] = 0; I[-8:] = 0; I[:, :8] = 0; I[:, -8:] = 0
+    outs = []
+    for variant in (0, 2):
+        out = torch.zeros((n, n), device="cuda")
+        abi.splat(I, Dx, Dy, out, margin=15, variant=variant)
+        outs.append(out)
+        assert abs(out.double().sum().item() / I.double().sum().item() - 1) < 1e-6
+    assert rel_l2(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["sub", "mid", "far", "huge"])
+def test_refract_phi_vs_reference(abi, golden, tag):
+    g = golden("fast_refraction")
+    pix, z, E, M = g["params"]
+    I32 = g["I"].astype(np.float32)
+    out = torch.zeros(I32.shape, device="cuda")
+    dxp = torch.zeros((I32.shape[0] + 30, I32.shape[1] + 30), device="cuda")
+    dyp = torch.zeros_like(dxp)
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    abi.refract_phi(dev(I32), dev(g["phi_" + tag], torch.float64), out, z, E, M, pix, 15, dxp, dyp, flag)
+    assert int(flag.item()) == 0
+    assert rel_l2(dxp.cpu().numpy(), g["Dx_" + tag]) < 1e-6
+    assert rel_l2(dyp.cpu().numpy(), g["Dy_" + tag]) < 1e-6
+    assert rel_l2(out.cpu().numpy(), g["out_" + tag]) < TOL
+    # v1 (margin 10) is the same map below its clamp
+    if tag != "huge":
+        out1 = torch.zeros(I32.shape, device="cuda")
+        abi.refract_phi(dev(I32), dev(g["phi_" + tag], torch.float64), out1, z, E, M, pix, 10)
+        assert rel_l2(out1.cpu().numpy(), g["outv1_" + tag]) < TOL
+
+
+def _layer_coeffs(deltas, betas, E, z, M, pix):
+    from paresis_b200 import hostmath as hm
+    k = hm.wavenumber(E * 1000)
+    s = hm.refraction_gradient_scale(z, M, pix)
+    return [d * s for d in deltas], [2 * k * b for b in betas]
+
+
+@pytest.mark.parametrize("shape", [(130, 290), (300, 257)])
+def test_refract_layers_vs_oracle(abi, shape):
+    """Experiment.py:463-474: membrane hop, then the fused sample + reference hop."""
+    rng = np.random.default_rng(17)
+    x = np.linspace(0, 5, shape[0])[:, None]
+    y = np.linspace(0, 5, shape[1])[None, :]
+    t_mem = (2e-4 * (1 + np.sin(3 * x) * np.cos(2.3 * y)) * (rng.random(shape) > 0.02)).astype(np.float32)
+    t_smp = (9e-4 * np.exp(-((x - 2.5) ** 2 + (y - 2.2) ** 2))).astype(np.float32)
+    E, pix, M, d2, d3 = 52.0, 2.9256, 1.0254, 1.6, 3.6
+    dm, bm, ds, bs = [5.97e-7], [5.37e-9], [9.52e-8], [4.4e-11]
+    i0 = 7500.0
+    # oracle, fp64, on the same fp32-rounded maps
+    tm64, ts64 = t_mem.astype(np.float64), t_smp.astype(np.float64)
+    i_m, phi_m = po.set_wave_rt(np.full(shape, i0), np.zeros(shape), [tm64], dm, bm, E)
+    i_bs, _, _ = po.fast_refraction(i_m, phi_m, d2, E, M, pix)
+    i_s, phi_ms = po.set_wave_rt(i_bs, phi_m, [ts64], ds, bs, E)
+    want_s, _, _ = po.fast_refraction(i_s, phi_ms, d3, E, M, pix)
+    want_r, _, _ = po.fast_refraction(i_bs.copy(), phi_m, d3, E, M, pix)
+    # GPU
+    tm, ts = dev(t_mem), dev(t_smp)
+    g2, a2 = _layer_coeffs(dm, bm, E, d2, M, pix)
+    ibs = torch.zeros(shape, device="cuda")
+    abi.refract_layers(None, i0, [(tm, g2[0], 0.0, a2[0])], ibs)
+    assert rel_l2(ibs.cpu().numpy(), i_bs) < TOL
+    g3m, _ = _layer_coeffs(dm, bm, E, d3, M, pix)
+    g3s, a3s = _layer_coeffs(ds, bs, E, d3, M, pix)
+    out_s = torch.zeros(shape, device="cuda")
+    out_r = torch.zeros(shape, device="cuda")
+    abi.refract_layers(ibs, 0.0, [(tm, g3m[0], g3m[0], 0.0), (ts, g3s[0], 0.0, a3s[0])], out_s, out_r)
+    assert rel_l2(out_r.cpu().numpy(), want_r) < TOL
+    assert rel_l2(out_s.cpu().numpy(), want_s) < TOL
+
+
+def test_transmission(abi, golden):
+    from paresis_b200 import hostmath as hm
+    g = golden("waves")
+    E = float(g["E"])
+    k = hm.wavenumber(E * 1000)
+    t = [dev(g["t"][0]), dev(g["t"][1])]
+    shape = g["I"].shape
+    i_out = torch.empty(shape, device="cuda")
+    phi_out = torch.empty(shape, device="cuda", dtype=torch.float64)
+    abi.transmit_rt(dev(g["I"]), dev(g["phi0"], torch.float64), t, [2 * k * b for b in g["beta"]],
+                    [k * d for d in g["delta"]], i_out, phi_out)
+    assert rel_l2(i_out.cpu().numpy(), g["I_rt"]) < 1e-6
+    assert rel_l2(phi_out.cpu().numpy(), g["phi_rt"]) < 1e-6
+    w_out = torch.empty(shape, device="cuda", dtype=torch.complex64)
+    abi.transmit_wave(dev(g["wave0"], torch.complex64), 0.0, t, [k * b for b in g["beta"]], [k * d for d in g["delta"]], w_out)
+    got = w_out.cpu().numpy()
+    assert np.abs(got - g["wave"]).max() / np.abs(g["wave"]).max() < 2e-5  # fp32 thickness carries ~1e-5 rad
+    assert rel_l2(np.abs(got) ** 2, np.abs(g["wave"]) ** 2) < 1e-6
+
+
+def test_fresnel_propagation(abi, golden):
+    from paresis_b200 import hostmath as hm
+    g = golden("waves")
+    E = float(g["E"])
+    nx, ny = g["wave"].shape
+    plan = abi.FresnelPlan(nx, ny, 15)
+    w_in = dev(g["wave"], torch.complex64)
+    for kcase in range(2):
+        z, M, pix = g["prop%d_cfg" % kcase]
+        hx, hy, phase = hm.fresnel_vectors(nx, ny, 15, (nx, ny), pix, z, E, M)
+        w_out = torch.empty((nx, ny), device="cuda", dtype=torch.complex64)
+        acc = torch.zeros((nx, ny), device="cuda")
+        plan.propagate(w_in, dev(hx, torch.complex64), dev(hy, torch.complex64), phase, w_out, acc)
+        want = g["prop%d" % kcase]
+        assert rel_l2(np.abs(w_out.cpu().numpy()) ** 2, np.abs(want) ** 2) < TOL
+        assert rel_l2(acc.cpu().numpy(), np.abs(want) ** 2) < TOL
+        # complex field incl. the global phase exp(ikz/M) (k z ~ 1e12 rad: only fp64 on the host can carry it)
+        assert np.abs(w_out.cpu().numpy() - want).max() / np.abs(want).max() < 1e-4
+    plan.close()
+
+
+def test_detection(abi, golden):
+    from paresis_b200 import hostmath as hm
+    g = golden("detector")
+    for kcase in range(int(g["n_det"])):
+        os_, d0, d1, fwhm, psf = g["det%d_cfg" % kcase]
+        os_, d0, d1 = int(os_), int(d0), int(d1)
+        img = dev(g["det%d_in" % kcase])
+        src = dev(hm.gaussian_1d(fwhm / 2.355)) if fwhm != 0 else None
+        pk = dev(hm.gaussian_1d(psf)) if psf != 0 else None
+        work = torch.empty(abi.detect_work_floats(d0 * os_, d1 * os_, os_, d0, d1), device="cuda")
+        out = torch.empty((d0, d1), device="cuda")
+        abi.detect(img, os_, d0, d1, src, pk, work, out)
+        assert rel_l2(out.cpu().numpy(), g["det%d_out" % kcase]) < 1e-6, kcase
+    out = torch.empty((30, 45), device="cuda")
+    abi.bin_sum(dev(g["resize_in"]), 30, 45, out)
+    assert rel_l2(out.cpu().numpy(), g["resize_2"]) < 1e-6
+    out = torch.empty((20, 30), device="cuda")
+    abi.bin_sum(dev(g["resize_in"]), 20, 30, out)
+    assert rel_l2(out.cpu().numpy(), g["resize_3"]) < 1e-6
+
+
+def test_membrane_and_samples(abi, golden):
+    from ref_harness import synthetic_sphere_rows
+    g = golden("geometry")
+    rows = synthetic_sphere_rows(0, 60000)
+    for tag in ("mem0", "mem1"):
+        mean_r, layers, dx, dy, pix, support, seed = g[tag + "_cfg"]
+        dx, dy, layers = int(dx), int(dy), int(layers)
+        tab, ex, ey = po.membrane_sphere_table(rows, float(mean_r), dx, dy, float(pix))
+        np.random.seed(int(seed))
+        offs = po.draw_membrane_offsets(layers, float(mean_r), ex, ey, dx, dy, float(pix))
+        margin, _ = po.membrane_margin(float(mean_r), float(pix))
+        out = torch.empty((dx, dy), device="cuda")
+        abi.raster_spheres(dev(tab, torch.float64), float(pix), offs, dx, dy, margin, out)
+        assert rel_l2(out.cpu().numpy(), g[tag][0]) < 1e-6, tag
+    r, dx, dy, pix = g["sphere_cfg"]
+    out = torch.empty((int(dx), int(dy)), device="cuda")
+    abi.sphere_map(float(r), int(dx), int(dy), float(pix), out)
+    assert rel_l2(out.cpu().numpy(), g["sphere"][0]) < 1e-6
+    for tag in ("cyl", "cyl2"):
+        r, ang, dx, dy, pix = g[tag + "_cfg"]
+        out = torch.empty((int(dx), int(dy)), device="cuda")
+        abi.cylinder_map(float(r), float(ang), int(dx), int(dy), float(pix), out)
+        assert rel_l2(out.cpu().numpy(), g[tag][0]) < 1e-6, tag
+
+
+def test_poisson_statistics(abi):
+    """rs.poisson (Detector.py:113-115) cannot be compared draw for draw (wall-clock seed);
+    check moments for small / medium / large lambda, a chi-square at low lambda, and the
+    counter-based reproducibility."""
+    from scipy import stats
+    n = 1 << 20
+    for lam in (0.3, 4.0, 9.99, 10.0, 37.5, 7500.0, 3.0e5):
+        expect = torch.full((n,), lam, device="cuda")
+        counts = torch.empty(n, device="cuda")
+        abi.poisson(expect, counts, 1234, 7)
+        c = counts.double()
+        m, v = c.mean().item(), c.var().item()
+        assert abs(m - lam) < 6 * np.sqrt(lam / n), (lam, m)
+        assert abs(v / lam - 1) < 6 * np.sqrt(2.0 / n) + 2.0 / lam / np.sqrt(n) + 1e-3, (lam, v)
+        assert torch.equal(c, torch.round(c)) and c.min().item() >= 0
+        if lam < 40:
+            kmax = int(stats.poisson.ppf(1 - 1e-7, lam)) + 1
+            obs = torch.bincount(counts.long(), minlength=kmax + 1).cpu().numpy().astype(np.float64)
+            pmf = stats.poisson.pmf(np.arange(len(obs)), lam) * n
+            keep = pmf > 20
+            chi2 = ((obs[keep] - pmf[keep]) ** 2 / pmf[keep]).sum()
+            assert chi2 < stats.chi2.ppf(1 - 1e-6, keep.sum()), (lam, chi2)
+    lam = torch.rand(4096, device="cuda") * 50
+    a = torch.empty(4096, device="cuda"); b = torch.empty(4096, device="cuda"); c2 = torch.empty(4096, device="cuda")
+    abi.poisson(lam, a, 5, 1); abi.poisson(lam, b, 5, 1); abi.poisson(lam, c2, 5, 2)
+    assert torch.equal(a, b) and not torch.equal(a, c2)
+    # sharding independence: the draw for pixel p does not depend on the launch extent
+    d = torch.empty(1000, device="cuda")
+    abi.poisson(lam[:1000].contiguous(), d, 5, 1)
+    assert torch.equal(d, a[:1000])
