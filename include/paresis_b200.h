@@ -60,11 +60,13 @@ int paresis_splat(const float* intensity, const float* dx, const float* dy, floa
  * displacement in pixels (:55-56) -> clean-up (:59-64) -> scatter (:77) in one kernel.
  * out[nx][ny] += result.  dx_pad / dy_pad (nullable) receive the cleaned displacement maps
  * at offset (margin, margin) of a pre-zeroed [(nx+2m)][(ny+2m)] array, which is what the
- * reference returns (:86).  phi is fp64 so that a phase of ~1e2-1e3 rad keeps its gradient. */
+ * reference returns (:86).  phi is fp64 so that a phase of ~1e2-1e3 rad keeps its gradient.
+ * clamp_px: rays displaced by more than this are dropped; <= 0 selects v2's rule |Dx| > nx,
+ * |Dy| > ny (:61-64), 1e3 is v1's (refractionFileNumba.py:46-49). */
 int paresis_refract_phi(const float* intensity, const double* phi, float* out,
                         float* dx_pad, float* dy_pad, int nx, int ny, int margin,
                         double distance_m, double energy_kev, double magnification, double pixel_um,
-                        int* flag, paresis_stream stream);
+                        double clamp_px, int* flag, paresis_stream stream);
 
 /* One projected-thickness map and its per-energy coefficients, formed in fp64 on the host:
  *   grad_obj / grad_ref : pixels of displacement per metre of 2-pixel thickness difference,
@@ -83,11 +85,14 @@ typedef struct {
  *   I_obj = I_in * exp(-sum atten_m t_m),  D_obj = sum grad_obj_m * d(t_m),  out_obj += scatter
  *   I_ref = I_in                          D_ref = sum grad_ref_m * d(t_m),  out_ref += scatter
  * intensity_in may be NULL (uniform `intensity_uniform`, e.g. I0 * flux).  out_ref may be NULL.
+ * dx_pad / dy_pad (both or neither; only with out_ref == NULL) receive the cleaned object-beam
+ * displacement at (margin, margin) of a pre-zeroed [(nx+2m)][(ny+2m)] array -- the Dx, Dy that
+ * Experiment.refraction returns (Experiment.py:492, :526).
  * Thickness is differenced first and scaled after, so uniform layers cancel exactly. */
 int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
                            const paresis_layer* layers_host, int n_layers,
-                           float* out_obj, float* out_ref, int nx, int ny, int margin,
-                           int* flag, paresis_stream stream);
+                           float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
+                           int nx, int ny, int margin, int* flag, paresis_stream stream);
 
 /* AnalyticalSample.setWaveRT as a stand-alone call (Sample.py:285-351, no dark-field branch):
  * I_out = I_in * exp(-sum atten_m t_m); phi_out = phi_in - sum phase_m t_m (phase_m = k delta_m).

@@ -55,8 +55,8 @@ def _load():
     lib.paresis_last_error.restype = ctypes.c_char_p
     sig = {
         "paresis_splat": [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp],
-        "paresis_refract_phi": [vp, vp, vp, vp, vp, ci, ci, ci, cd, cd, cd, cd, vp, vp],
-        "paresis_refract_layers": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, ci, ci, ci, vp, vp],
+        "paresis_refract_phi": [vp, vp, vp, vp, vp, ci, ci, ci, cd, cd, cd, cd, cd, vp, vp],
+        "paresis_refract_layers": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, vp, vp, ci, ci, ci, vp, vp],
         "paresis_transmit_rt": [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(cd), ctypes.POINTER(cd), ci, vp, vp, sz, vp],
         "paresis_transmit_wave": [vp, cf, ctypes.POINTER(vp), ctypes.POINTER(cd), ctypes.POINTER(cd), ci, vp, sz, vp],
         "paresis_fresnel_plan_create": [ci, ci, ci, ctypes.POINTER(vp)],
@@ -122,16 +122,17 @@ def splat(intensity, dx, dy, out, margin=0, variant=2, flag=None):
 
 
 def refract_phi(intensity, phi, out, distance, energy_kev, magnification, pixel_um, margin=REFRACTION_MARGIN,
-                dx_pad=None, dy_pad=None, flag=None):
+                dx_pad=None, dy_pad=None, flag=None, clamp_px=0.0):
     nx, ny = intensity.shape
     _check(lib.paresis_refract_phi(_ptr(intensity, torch.float32), _ptr(phi, torch.float64), _ptr(out, torch.float32),
                                    _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
                                    float(distance), float(energy_kev), float(magnification), float(pixel_um),
-                                   _ptr(flag, torch.int32), _stream()), "paresis_refract_phi")
+                                   float(clamp_px), _ptr(flag, torch.int32), _stream()), "paresis_refract_phi")
     _count()
 
 
-def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None):
+def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None,
+                   dx_pad=None, dy_pad=None):
     """layers: list of (thickness tensor, grad_obj, grad_ref, atten)."""
     n = len(layers)
     arr = (Layer * n)()
@@ -141,7 +142,8 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
         _ptr(t, torch.float32)
     nx, ny = out_obj.shape
     _check(lib.paresis_refract_layers(_ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n,
-                                      _ptr(out_obj, torch.float32), _ptr(out_ref, torch.float32), nx, ny, margin,
+                                      _ptr(out_obj, torch.float32), _ptr(out_ref, torch.float32),
+                                      _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
                                       _ptr(flag, torch.int32), _stream()), "paresis_refract_layers")
     _count()
 

@@ -70,15 +70,16 @@ struct RefractArgs {
     float* dx_pad;   // optional: cleaned object-beam displacement, stored at (+margin, +margin)
     float* dy_pad;
     Frame f;
+    float clamp_x, clamp_y;   // rays with |D| above these are dropped (v2: nx, ny; v1: 1e3)
     int rows;
     int* flag;
 };
 
 // refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
-__device__ __forceinline__ void clean(float& v, float& dx, float& dy, int nx, int ny) {
+__device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, float cy) {
     if (fabsf(dx) < 1e-12f) dx = 0.f;
     if (fabsf(dy) < 1e-12f) dy = 0.f;
-    const bool bx = fabsf(dx) > (float)nx, by = fabsf(dy) > (float)ny;
+    const bool bx = fabsf(dx) > cx, by = fabsf(dy) > cy;
     if (bx | by) v = 0.f;
     if (bx) dx = 0.f;
     if (by) dy = 0.f;
@@ -147,8 +148,8 @@ refract_kernel(const RefractArgs<T> a) {
         }
         float vo = ATT ? vin * expf(-arg) : vin;   // Sample.py:347
         float vr = vin;
-        clean(vo, dxo, dyo, f.nx, f.ny);
-        if (DUAL) clean(vr, dxr, dyr, f.nx, f.ny);
+        clean(vo, dxo, dyo, a.clamp_x, a.clamp_y);
+        if (DUAL) clean(vr, dxr, dyr, a.clamp_x, a.clamp_y);
         if (WRITE_D && live) {
             const size_t pp = (size_t)(i + f.margin) * (f.ny + 2 * f.margin) + (j + f.margin);
             a.dx_pad[pp] = dxo;
@@ -195,10 +196,11 @@ static int launch_refract(const RefractArgs<T>& a, bool write_d, cudaStream_t s)
 template <int NM>
 static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
     const bool dual = a.out_ref != nullptr, has_i = a.I_in != nullptr;
+    const bool wd = a.dx_pad != nullptr;
     if (dual) return has_i ? launch_refract<float, NM, true, true, true>(a, false, s)
                            : launch_refract<float, NM, true, false, true>(a, false, s);
-    return has_i ? launch_refract<float, NM, false, true, true>(a, false, s)
-                 : launch_refract<float, NM, false, false, true>(a, false, s);
+    return has_i ? launch_refract<float, NM, false, true, true>(a, wd, s)
+                 : launch_refract<float, NM, false, false, true>(a, wd, s);
 }
 
 }  // namespace paresis
@@ -229,7 +231,7 @@ extern "C" int paresis_splat(const float* intensity, const float* dx, const floa
 extern "C" int paresis_refract_phi(const float* intensity, const double* phi, float* out,
                                    float* dx_pad, float* dy_pad, int nx, int ny, int margin,
                                    double distance_m, double energy_kev, double magnification, double pixel_um,
-                                   int* flag, paresis_stream stream) {
+                                   double clamp_px, int* flag, paresis_stream stream) {
     if (!intensity || !phi || !out || ((dx_pad == nullptr) != (dy_pad == nullptr))) {
         set_last_error("paresis_refract_phi: null pointer");
         return PARESIS_ERR_ARG;
@@ -248,6 +250,8 @@ extern "C" int paresis_refract_phi(const float* intensity, const double* phi, fl
     a.dx_pad = dx_pad;
     a.dy_pad = dy_pad;
     a.f = Frame{nx, ny, margin};
+    a.clamp_x = clamp_px > 0 ? (float)clamp_px : (float)nx;
+    a.clamp_y = clamp_px > 0 ? (float)clamp_px : (float)ny;
     a.rows = pick_rows(nx, ny);
     a.flag = flag;
     return launch_refract<double, 1, false, true, false>(a, dx_pad != nullptr, (cudaStream_t)stream);
@@ -255,10 +259,14 @@ extern "C" int paresis_refract_phi(const float* intensity, const double* phi, fl
 
 extern "C" int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
                                       const paresis_layer* layers_host, int n_layers,
-                                      float* out_obj, float* out_ref, int nx, int ny, int margin,
-                                      int* flag, paresis_stream stream) {
+                                      float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
+                                      int nx, int ny, int margin, int* flag, paresis_stream stream) {
     if (!layers_host || !out_obj || n_layers < 1 || n_layers > PARESIS_MAX_LAYERS) {
         set_last_error("paresis_refract_layers: need 1..%d layers and an output", PARESIS_MAX_LAYERS);
+        return PARESIS_ERR_ARG;
+    }
+    if (((dx_pad == nullptr) != (dy_pad == nullptr)) || (dx_pad && out_ref)) {
+        set_last_error("paresis_refract_layers: dx_pad/dy_pad come together and only without out_ref");
         return PARESIS_ERR_ARG;
     }
     int rc = check_frame(nx, ny, margin);
@@ -275,7 +283,11 @@ extern "C" int paresis_refract_layers(const float* intensity_in, float intensity
     a.I_uniform = intensity_uniform;
     a.out_obj = out_obj;
     a.out_ref = out_ref;
+    a.dx_pad = dx_pad;
+    a.dy_pad = dy_pad;
     a.f = Frame{nx, ny, margin};
+    a.clamp_x = (float)nx;
+    a.clamp_y = (float)ny;
     a.rows = pick_rows(nx, ny);
     a.flag = flag;
     cudaStream_t s = (cudaStream_t)stream;

@@ -1,0 +1,293 @@
+"""Device-resident image formation for one membrane position.
+
+This is the B200 execution of ``Experiment.computeSampleAndReferenceImages_RT`` /
+``_Fresnel`` (reference Experiment.py:407-526 / :279-405): the per-energy loop runs as a
+short sequence of fused CUDA kernels on one stream, the accumulators never leave HBM, and
+only the detector images come back to the host.  PyTorch provides device memory and streams;
+all arithmetic is in ``libparesis_b200.so`` (C ABI, ``include/paresis_b200.h``).
+
+The host shim (``paresis_b200/CodePython/Experiment.py``) builds a :class:`Scene` from the
+XML-derived objects and calls :meth:`ImageFormation.compute_rt` / ``compute_fresnel``.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi as abi
+from . import hostmath as hm
+
+IMAGES = ("sample", "reference", "propag", "white")
+
+
+class Layer:
+    """One material of an object: a device thickness map (metres) or a uniform thickness."""
+
+    __slots__ = ("map", "uniform", "delta", "beta")
+
+    def __init__(self, thickness, delta, beta):
+        # delta / beta: {energy_keV: value}
+        if isinstance(thickness, torch.Tensor):
+            self.map, self.uniform = thickness, None
+        else:
+            self.map, self.uniform = None, float(thickness)
+        self.delta, self.beta = delta, beta
+
+
+class Scene:
+    """Everything the per-energy loop reads (products of Experiment.__init__, Experiment.py:81-100).
+
+    ``membrane`` may mix mapped and uniform layers (the support plate is uniform: it only
+    attenuates); ``sample`` layers must all be maps."""
+
+    def __init__(self, study_dims, study_pixel_um, oversampling, det_dims, det_pixel_um, psf_sigma,
+                 d_source_membrane, d_membrane_object, d_object_detector, mean_shot_count,
+                 spectrum, source_size_um, energy_sampling, thresholds, membrane, sample,
+                 common_factor=None, plate_factor=None):
+        self.study_dims = (int(study_dims[0]), int(study_dims[1]))
+        self.study_pixel_um = float(study_pixel_um)
+        self.os = int(oversampling)
+        self.det_dims = (int(det_dims[0]), int(det_dims[1]))
+        self.det_pixel_um = float(det_pixel_um)
+        self.psf_sigma = float(psf_sigma)
+        self.d1, self.d2, self.d3 = float(d_source_membrane), float(d_membrane_object), float(d_object_detector)
+        self.magnification = (self.d1 + self.d3 + self.d2) / (self.d1 + self.d2)
+        self.mean_shot_count = float(mean_shot_count)
+        self.spectrum = [(float(e), float(w)) for e, w in spectrum]
+        self.source_size_um = float(source_size_um)
+        self.energy_sampling = float(energy_sampling)
+        self.thresholds = list(thresholds)   # already closed by the last energy (Experiment.py:429)
+        self.membrane = list(membrane)
+        self.sample = list(sample)
+        # per-energy scalar factors on the incident intensity: air volume and scintillator
+        # efficiency (Experiment.py:452-459); detector protection plate (:478-480, :494-496)
+        self.common_factor = common_factor or (lambda e: 1.0)
+        self.plate_factor = plate_factor or (lambda e: 1.0)
+
+    def effective_source_fwhm(self):
+        """Experiment.py:503 (FWHM in oversampled pixels)."""
+        return self.source_size_um * self.d3 / (self.d1 + self.d2) / self.det_pixel_um * self.os
+
+
+class InsaneValues(Exception):
+    pass
+
+
+class ImageFormation:
+    """Owns the scratch buffers of one GPU and runs membrane positions one after another."""
+
+    def __init__(self, study_dims, oversampling, det_dims, device=None, seed=None, poisson=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("paresis_b200 needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.nx, self.ny = int(study_dims[0]), int(study_dims[1])
+        self.os = int(oversampling)
+        self.det_x, self.det_y = int(det_dims[0]), int(det_dims[1])
+        self.poisson = poisson
+        # Detector.py:113 seeds from the wall clock; so do we unless told otherwise
+        self.seed = int(np.floor(time.time() * 100 % (2 ** 32 - 1))) if seed is None else int(seed)
+        f32 = dict(device=self.device, dtype=torch.float32)
+        n = (self.nx, self.ny)
+        self.i_bs = torch.empty(n, **f32)
+        self.acc = {k: torch.zeros(n, **f32) for k in IMAGES}
+        self.work = torch.empty(abi.detect_work_floats(self.nx, self.ny, self.os, self.det_x, self.det_y), **f32)
+        self.expect = torch.empty((self.det_x, self.det_y), **f32)
+        self.flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.means = torch.zeros(256, device=self.device, dtype=torch.float64)
+        self.dx_pad = None
+        self.dy_pad = None
+        self._kernels = {}
+        self._plan = None
+        self._vectors = {}
+        self._waves = None
+
+    # ------------------------------------------------------------------ helpers
+    def _gauss(self, sigma):
+        key = round(float(sigma), 12)
+        if key not in self._kernels:
+            if hm.gaussian_half_width(sigma) == 0:
+                self._kernels[key] = None      # 1x1 kernel == identity (round(3*sigma) == 0, Detector.py:212)
+            else:
+                self._kernels[key] = torch.as_tensor(hm.gaussian_1d(sigma), device=self.device, dtype=torch.float32)
+        return self._kernels[key]
+
+    def detect(self, image, fwhm, psf_sigma, sequence, out):
+        """Detector.detection (Detector.py:79-119): device image -> ``out`` (device, detector dims)."""
+        src = self._gauss(fwhm / 2.355) if fwhm != 0 else None
+        psf = self._gauss(psf_sigma) if psf_sigma != 0 else None
+        if self.poisson:
+            abi.detect(image, self.os, self.det_x, self.det_y, src, psf, self.work, self.expect)
+            abi.poisson(self.expect, out, self.seed, sequence)
+        else:
+            abi.detect(image, self.os, self.det_x, self.det_y, src, psf, self.work, out)
+
+    def check_flag(self):
+        """The reference's NaN / 'insane values' guard (refractionFileNumba2.py:81-82), checked lazily."""
+        if int(self.flag.item()) & abi.FLAG_NONFINITE:
+            self.flag.zero_()
+            raise InsaneValues("The calculated intensity refractive includes some nans or insane values")
+
+    @staticmethod
+    def _split(layers, energy):
+        """-> maps [(tensor, delta, beta)], sum(beta*t) and sum(delta*t) of the uniform layers."""
+        maps, ub, ud = [], 0.0, 0.0
+        for L in layers:
+            d, b = L.delta.get(energy, 0.0), L.beta.get(energy, 0.0)   # a missing energy leaves 0 (Sample.py:303-319)
+            if L.map is not None:
+                maps.append((L.map, d, b))
+            else:
+                ub += b * L.uniform
+                ud += d * L.uniform
+        return maps, ub, ud
+
+    def _new_outputs(self, nbins):
+        return {k: torch.zeros((nbins, self.det_x, self.det_y), device=self.device, dtype=torch.float32) for k in IMAGES}
+
+    def _reset(self, n_energies):
+        for a in self.acc.values():
+            a.zero_()
+        if n_energies > self.means.numel():
+            self.means = torch.zeros(n_energies, device=self.device, dtype=torch.float64)
+
+    def _close_bin(self, scene, out, ibin, point_num, first, white_sum, sequence_base):
+        fwhm = scene.effective_source_fwhm()
+        seq = ((sequence_base + point_num) << 16) + ibin * 4
+        self.detect(self.acc["sample"], fwhm, scene.psf_sigma, seq + 0, out["sample"][ibin])
+        self.detect(self.acc["reference"], fwhm, scene.psf_sigma, seq + 1, out["reference"][ibin])
+        if first:
+            self.detect(self.acc["propag"], fwhm, scene.psf_sigma, seq + 2, out["propag"][ibin])
+            abi.fill(self.acc["white"], white_sum)
+            self.detect(self.acc["white"], fwhm, scene.psf_sigma, seq + 3, out["white"][ibin])
+
+    def _mean_energy(self, energies, bin_starts):
+        """Experiment.py:485-486, :523 from the running means of the reference accumulator."""
+        r = self.means[:len(energies)].cpu().numpy()
+        per = r.copy()
+        for i in range(1, len(per)):
+            if i not in bin_starts:
+                per[i] = r[i] - r[i - 1]
+        return float(np.dot(per, energies)), float(per.sum())
+
+    # ------------------------------------------------------------------ ray tracing
+    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0):
+        """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526).
+
+        Returns a dict of device tensors [nbins, det_x, det_y] (sample, reference, propag, white)
+        plus ``mean_energy`` = (sum E*mean, sum mean) of Experiment.py:485-486."""
+        s = scene
+        out = self._new_outputs(len(s.thresholds))
+        self._reset(len(s.spectrum))
+        first = point_num == 0
+        if first and want_displacement and self.dx_pad is None:
+            self.dx_pad = torch.zeros((self.nx + 30, self.ny + 30), device=self.device, dtype=torch.float32)
+            self.dy_pad = torch.zeros_like(self.dx_pad)
+        g2 = hm.refraction_gradient_scale(s.d2, s.magnification, s.study_pixel_um)
+        g3 = hm.refraction_gradient_scale(s.d3, s.magnification, s.study_pixel_um)
+        ibin, white_sum, bin_starts = 0, 0.0, {0}
+        for ie, (energy, flux) in enumerate(s.spectrum):
+            k = hm.wavenumber(energy * 1000)
+            i0 = s.mean_shot_count / s.os ** 2 * flux * s.common_factor(energy)      # :438, :451-459
+            plate = s.plate_factor(energy)
+            mem_maps, mem_ub, _ = self._split(s.membrane, energy)
+            smp_maps, smp_ub, _ = self._split(s.sample, energy)
+            if smp_ub != 0.0 or not mem_maps or not smp_maps or len(mem_maps) + len(smp_maps) > abi.MAX_LAYERS:
+                raise NotImplementedError("scene needs 1+ membrane maps, sample maps only, at most %d maps per hop"
+                                          % abi.MAX_LAYERS)
+            # membrane -> object plane (:463-466); uniform layers and the plate only scale the beam
+            self.i_bs.zero_()
+            abi.refract_layers(None, i0 * np.exp(-2 * k * mem_ub) * plate,
+                               [(t, d * g2, 0.0, 2 * k * b) for t, d, b in mem_maps], self.i_bs, flag=self.flag)
+            # object -> detector: sample beam and reference beam in one pass over I_bs (:469-474)
+            layers = [(t, d * g3, d * g3, 0.0) for t, d, b in mem_maps] + \
+                     [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps]
+            abi.refract_layers(self.i_bs, 0.0, layers, self.acc["sample"], self.acc["reference"], flag=self.flag)
+            abi.mean(self.acc["reference"], self.means[ie:ie + 1])
+            if first:
+                # the sample alone (:490-498); the white field is the incident beam itself
+                wd = want_displacement and ie == len(s.spectrum) - 1
+                if wd:
+                    self.dx_pad.zero_()
+                    self.dy_pad.zero_()
+                abi.refract_layers(None, i0 * plate, [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps],
+                                   self.acc["propag"], flag=self.flag,
+                                   dx_pad=self.dx_pad if wd else None, dy_pad=self.dy_pad if wd else None)
+                white_sum += i0 * plate
+            if energy > s.thresholds[ibin] - s.energy_sampling / 2:                  # :501
+                self._close_bin(s, out, ibin, point_num, first, white_sum, sequence_base)
+                ibin += 1
+                if ie + 1 < len(s.spectrum):
+                    for a in self.acc.values():
+                        a.zero_()
+                    white_sum = 0.0
+                    bin_starts.add(ie + 1)
+        out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
+        self.check_flag()
+        return out
+
+    # ------------------------------------------------------------------ Fresnel
+    def _fresnel_setup(self):
+        if self._plan is None:
+            self._plan = abi.FresnelPlan(self.nx, self.ny, 15)
+            c64 = dict(device=self.device, dtype=torch.complex64)
+            self._waves = [torch.empty((self.nx, self.ny), **c64) for _ in range(2)]
+
+    def _transfer(self, scene, distance, energy, magnification):
+        key = (distance, energy, magnification)
+        if key not in self._vectors:
+            hx, hy, phase = hm.fresnel_vectors(self.nx, self.ny, 15, scene.study_dims, scene.study_pixel_um,
+                                               distance, energy, magnification)
+            self._vectors[key] = (torch.as_tensor(hx, device=self.device), torch.as_tensor(hy, device=self.device), phase)
+        return self._vectors[key]
+
+    def propagate(self, scene, wave_in, distance, energy, magnification, wave_out=None, intensity_acc=None):
+        """Experiment.wavePropagation (Experiment.py:219-252) on device fields."""
+        self._fresnel_setup()
+        hx, hy, phase = self._transfer(scene, distance, energy, magnification)
+        # |.|^2 ignores the global phase; a returned field carries it (formed in fp64 on the host)
+        self._plan.propagate(wave_in, hx, hy, phase if wave_out is not None else 1.0, wave_out, intensity_acc)
+
+    def compute_fresnel(self, scene, point_num, sequence_base=0):
+        """Experiment.computeSampleAndReferenceImages_Fresnel (Experiment.py:279-405)."""
+        s = scene
+        self._fresnel_setup()
+        out = self._new_outputs(len(s.thresholds))
+        self._reset(len(s.spectrum))
+        first = point_num == 0
+        w_a, w_b = self._waves
+        mag_mem_obj = (s.d1 + s.d2) / s.d1                                            # :340
+        ibin, white_sum, bin_starts = 0, 0.0, {0}
+        for ie, (energy, flux) in enumerate(s.spectrum):
+            k = hm.wavenumber(energy * 1000)
+            i0 = s.mean_shot_count / s.os ** 2 * flux * s.common_factor(energy)       # :308, :320-333
+            plate = s.plate_factor(energy)
+            amp = float(np.sqrt(i0 * plate))   # the plate scales every intensity linearly (:352-356)
+            mem_maps, mem_ub, _ = self._split(s.membrane, energy)
+            smp_maps, smp_ub, _ = self._split(s.sample, energy)
+            if smp_ub != 0.0 or not mem_maps or not smp_maps:
+                raise NotImplementedError("scene needs 1+ membrane maps and sample maps only")
+            # after the membrane (:338); uniform layers: attenuation folded in, constant phase dropped
+            abi.transmit_wave(None, amp * np.exp(-k * mem_ub), [t for t, _, _ in mem_maps],
+                              [k * b for _, _, b in mem_maps], [k * d for _, d, _ in mem_maps], w_a)
+            # reference beam: membrane -> detector in one hop (:349, :354)
+            self.propagate(s, w_a, s.d3 + s.d2, energy, s.magnification, intensity_acc=self.acc["reference"])
+            # sample beam: membrane -> object (:340-341), through the sample (:344), -> detector (:348)
+            self.propagate(s, w_a, s.d2, energy, mag_mem_obj, wave_out=w_b)
+            abi.transmit_wave(w_b, 0.0, [t for t, _, _ in smp_maps], [k * b for _, _, b in smp_maps],
+                              [k * d for _, d, _ in smp_maps], w_b)
+            self.propagate(s, w_b, s.d3, energy, s.magnification, intensity_acc=self.acc["sample"])
+            abi.mean(self.acc["reference"], self.means[ie:ie + 1])
+            if first:
+                abi.transmit_wave(None, amp, [t for t, _, _ in smp_maps], [k * b for _, _, b in smp_maps],
+                                  [k * d for _, d, _ in smp_maps], w_b)               # :365
+                self.propagate(s, w_b, s.d3, energy, s.magnification, intensity_acc=self.acc["propag"])
+                white_sum += amp * amp                                                # :372-375
+            if energy > s.thresholds[ibin] - s.energy_sampling / 2:                   # :378
+                self._close_bin(s, out, ibin, point_num, first, white_sum, sequence_base)
+                ibin += 1
+                if ie + 1 < len(s.spectrum):
+                    for a in self.acc.values():
+                        a.zero_()
+                    white_sum = 0.0
+                    bin_starts.add(ie + 1)
+        out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
+        return out

@@ -1,0 +1,148 @@
+"""Projected-thickness maps generated and kept on the GPU.
+
+Host logic of Samples/getMembraneFromFile.py:60-171 and Samples/createSampGeom.py:15-107
+(file parsing, rescaling, stitching, the ``np.random.randint`` draws in the reference's
+order); the per-pixel work is in csrc/geometry.cu.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _cabi as abi
+from .host_api import device
+
+
+class DeviceGeometry:
+    """Per-material thickness maps (metres) in HBM; uniform layers are kept as scalars.
+
+    Quacks like the ``[n_mat, N, N]`` ndarray PARESIS stores in ``Sample.myGeometry`` for the
+    accesses it makes: ``len``, ``.ndim``, ``.shape``, ``geom[m]`` (float32 host copy of one
+    map, what main.py:99 saves) and ``np.asarray(geom)`` (float64 stack)."""
+
+    ndim = 3
+
+    def __init__(self, entries, shape):
+        self.entries = list(entries)          # torch.Tensor [N, N] float32 | float (uniform thickness)
+        self.map_shape = (int(shape[0]), int(shape[1]))
+
+    @property
+    def shape(self):
+        return (len(self.entries),) + self.map_shape
+
+    def __len__(self):
+        return len(self.entries)
+
+    def __getitem__(self, m):
+        e = self.entries[m]
+        if isinstance(e, torch.Tensor):
+            return e.cpu().numpy()
+        return np.full(self.map_shape, e, dtype=np.float32)
+
+    def __array__(self, dtype=None, copy=None):
+        stack = np.stack([np.asarray(self[m], dtype=np.float64) for m in range(len(self.entries))])
+        return stack.astype(dtype) if dtype is not None else stack
+
+    def device_entries(self, materialise=False):
+        out = []
+        for e in self.entries:
+            if materialise and not isinstance(e, torch.Tensor):
+                e = torch.full(self.map_shape, float(e), device=device(), dtype=torch.float32)
+            out.append(e)
+        return out
+
+
+def from_host(array):
+    """Upload a user-supplied [n_mat, N, N] array; flat maps become uniform scalars."""
+    arr = np.asarray(array)
+    if arr.ndim != 3:
+        raise Exception("Sample Geometry has the wrong nb of dim [material, x, y]")   # Sample.py:264
+    entries = []
+    for m in range(arr.shape[0]):
+        lo, hi = float(arr[m].min()), float(arr[m].max())
+        if lo == hi:
+            entries.append(lo)
+        else:
+            entries.append(torch.as_tensor(np.ascontiguousarray(arr[m], dtype=np.float32)).to(device()))
+    return DeviceGeometry(entries, arr.shape[1:])
+
+
+# ---------------------------------------------------------------------------- membrane
+_MEMBRANE_FILE = "Samples/Membranes/CuSn.txt"
+_sphere_cache = {}
+
+
+def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
+    """getMembraneFromFile.py:84-124: load, rescale to the wanted mean radius, move the origin to
+    the top-left corner, tile along x then y until the list covers the field of view."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size, mean_radius, dim_x, dim_y, pix, torch.cuda.current_device())
+    if key in _sphere_cache:
+        return _sphere_cache[key]
+    if path.split('/')[-1] != 'CuSn.txt':
+        raise Exception("Enter segmented membrane size ")                               # :90
+    corr = mean_radius / 12.8
+    ext_x = int(np.floor(8102)) * corr + mean_radius
+    ext_y = int(np.floor(9740)) * corr + mean_radius
+    with open(path) as fh:
+        tab = np.asarray(json.load(fh), dtype=np.float64) * corr
+    tab[:, 1] += ext_x / 2
+    tab[:, 0] += ext_y / 2
+    base, step = tab.copy(), ext_x
+    while ext_x / pix - dim_x < 0:
+        print("segmented membrane too small: proceeding with stitching along x")
+        shifted = base.copy()
+        shifted[:, 1] += ext_x
+        tab = np.concatenate((tab, shifted), axis=0)
+        ext_x += step
+    base, step = tab.copy(), ext_y
+    while ext_y / pix - dim_y < 0:
+        print("segmented membrane too small: proceeding with stitching along y")
+        shifted = base.copy()
+        shifted[:, 0] += ext_y
+        tab = np.concatenate((tab, shifted), axis=0)
+        ext_y += step
+    dev_tab = torch.as_tensor(np.ascontiguousarray(tab)).to(device())
+    _sphere_cache.clear()
+    _sphere_cache[key] = (dev_tab, ext_x, ext_y)
+    return _sphere_cache[key]
+
+
+def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None):
+    """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171).
+
+    Two ``np.random.randint`` draws per layer, x first, from numpy's global stream (:139-140),
+    so ``np.random.seed`` reproduces the reference's membrane positions."""
+    dim_x, dim_y = int(dim_x), int(dim_y)
+    margin = int(np.ceil(10 * sample.myMeanSphereRadius / pix))
+    margin2 = int(np.floor(margin / 2))
+    table, ext_x, ext_y = _sphere_table(_MEMBRANE_FILE, sample.myMeanSphereRadius, dim_x, dim_y, pix)
+    offsets = []
+    for _ in range(sample.myNbOfLayers):
+        ox = np.random.randint(margin2, ext_x / pix - dim_x - margin2)
+        oy = np.random.randint(margin2, ext_y / pix - dim_y - margin2)
+        offsets.append((int(ox), int(oy)))
+    grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)
+    abi.raster_spheres(table, pix, offsets, dim_x, dim_y, margin, grains)
+    params = {'Average sphere radius': (sample.myMeanSphereRadius, 'um'),
+              'Number of layers': (sample.myNbOfLayers, ''),
+              'Support total thickness': (support_um, 'um')}
+    return DeviceGeometry([grains, support_um * 1e-6], (dim_x, dim_y)), params
+
+
+# ---------------------------------------------------------------------------- samples
+def sample_sphere(radius_um, dim_x, dim_y, pix):
+    """CreateSampleSphere arithmetic (createSampGeom.py:41-53)."""
+    out = torch.empty((int(dim_x), int(dim_y)), device=device(), dtype=torch.float32)
+    abi.sphere_map(radius_um, int(dim_x), int(dim_y), pix, out)
+    return DeviceGeometry([out], (dim_x, dim_y))
+
+
+def sample_cylinder(radius_um, orientation_deg, dim_x, dim_y, pix):
+    """CreateSampleCylindre arithmetic (createSampGeom.py:87-106), rotation included."""
+    if 2 * radius_um / pix > 2 * dim_x or 2 * radius_um / pix > 2 * dim_y:
+        raise Exception('The sample is too big for the detector field of view (increase dimX, dimY)')
+    out = torch.empty((int(dim_x), int(dim_y)), device=device(), dtype=torch.float32)
+    abi.cylinder_map(radius_um, orientation_deg, int(dim_x), int(dim_y), pix, out)
+    return DeviceGeometry([out], (dim_x, dim_y))

@@ -1,0 +1,158 @@
+"""End-to-end parity of the drop-in shim against the reference's own images.
+
+Same flow as PARESIS's main.py:63-71 (new membrane per point, then compute), Poisson noise
+off on both sides, same seeds for the membrane offsets.  Goldens come from the unmodified
+reference (oracle/make_golden.py).  Bound: 1e-5 relative L2 (north star).
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from paresis_b200 import workspace
+    ws = workspace.make_workspace(str(tmp_path_factory.mktemp("ws")))
+    old = os.getcwd()
+    workspace.enter(ws)
+    yield importlib.import_module("Experiment")
+    os.chdir(old)
+
+
+CASES = [
+    ("e2e_rt_cylinder", "Fil_Nylon_ID17", "RayT"),
+    ("e2e_rt_sphere", "Small_sphere_mono", "RayT"),
+    ("e2e_rt_poly3", "B200_small_poly3", "RayT"),
+    ("e2e_fresnel_sphere", "Small_sphere_mono", "Fresnel"),
+]
+
+
+@pytest.mark.parametrize("gold,name,model", CASES)
+def test_matches_reference_images(shim, golden, gold, name, model):
+    g = golden(gold)
+    d = dict(experimentName=name, filepath="unused/", overSampling=2, nbExpPoints=2, simulation_type=model,
+             expID="t", poissonNoise=False)
+    e = shim.Experiment(d)
+    assert np.allclose(d["magnification"], 145.2 / 141.6)
+    # the delta/beta the shim derived are the ones the reference used
+    for m in range(2):
+        assert np.allclose([v for _, v in e.myMembrane.delta[m]], g["membrane_db"][:, 1 + m], rtol=1e-12)
+        assert np.allclose([v for _, v in e.myMembrane.beta[m]], g["membrane_db"][:, 3 + m], rtol=1e-12)
+    probe = g["sample_t_probe"]
+    st = np.asarray(e.mySampleofInterest.myGeometry)
+    assert st.ndim == 3 and abs(st.sum() / probe[0] - 1) < 1e-6
+    for point in (0, 1):
+        np.random.seed(int(g["membrane_seed_p%d" % point]))
+        e.myMembrane.myGeometry = []
+        e.myMembrane.getMyGeometry(e.exp_dict['studyDimensions'], e.myMembrane.membranePixelSize, 2, point, 2)
+        mt = e.myMembrane.myGeometry[0]
+        mp = g["membrane_probe_p%d" % point]
+        assert abs(mt.astype(np.float64).sum() / mp[0] - 1) < 1e-6 and abs(mt[5, 9] / mp[2] - 1) < 1e-6 if mp[2] else True
+        if model == "RayT":
+            res = e.computeSampleAndReferenceImages_RT(point)
+            assert len(res) == 7 and res[6].shape == tuple(e.exp_dict['studyDimensions'])
+        else:
+            res = e.computeSampleAndReferenceImages_Fresnel(point)
+            assert len(res) == 4
+        sample, ref, propag, white = res[:4]
+        assert sample.dtype == np.float64 and sample.shape == g["sample_p%d" % point].shape
+        assert rel_l2(ref, g["reference_p%d" % point]) < TOL
+        assert rel_l2(sample, g["sample_p%d" % point]) < TOL
+        if point == 0:
+            assert rel_l2(propag, g["propag_p0"]) < TOL
+            assert rel_l2(white, g["white_p0"]) < TOL
+            if model == "RayT":
+                assert res[4].shape == (st.shape[1] + 30, st.shape[2] + 30)
+                # auxiliary output (main.py discards it): differences of fp32 thickness maps carry ~6e-8 * t/dt
+                assert rel_l2(res[4][::8, ::8], g["Dx_p0_s8"]) < 2e-4 and rel_l2(res[5][::8, ::8], g["Dy_p0_s8"]) < 2e-4
+        else:
+            assert not propag.any() and not white.any()
+    assert abs(e.exp_dict["meanEnergy"] / float(g["mean_energy"]) - 1) < 1e-5
+    # main.py:84-85 relies on the in-place bin closing
+    assert e.myDetector.det_param["myBinsThersholds"][-1] == e.mySource.mySpectrum[-1][0]
+
+
+def test_api_pieces_and_errors(shim, golden):
+    """The module-level functions keep their numpy-in / numpy-out contracts."""
+    r2 = importlib.import_module("refractionFileNumba2")
+    r1 = importlib.import_module("refractionFileNumba")
+    det = importlib.import_module("Detector")
+    g = golden("fast_refraction")
+    pix, z, E, M = g["params"]
+    out, dx, dy = r2.fastRefraction(g["I"].copy(), g["phi_mid"], z, E, M, pix)
+    assert out.dtype == np.float64 and dx.shape == (127, 143)
+    assert rel_l2(out, g["out_mid"]) < TOL and rel_l2(dx, g["Dx_mid"]) < 1e-6
+    out1, dx1, _ = r1.fastRefraction(g["I"].copy(), g["phi_mid"], z, E, M, pix)
+    assert dx1.shape == (117, 133) and rel_l2(out1, g["outv1_mid"]) < TOL
+    bad = g["I"].copy(); bad[4, 4] = np.nan
+    with pytest.raises(Exception, match="nans or insane values"):
+        r2.fastRefraction(bad, g["phi_mid"], z, E, M, pix)
+    k = golden("splat_kernel")
+    acc = np.zeros((37, 41))
+    ret = r2.fastloopNumba(37, 41, k["I_b"], acc, k["Dy_b"], k["Dx_b"], None, None)
+    assert ret is acc and rel_l2(acc, k["out_b"]) < 2e-6
+    d = golden("detector")
+    assert np.allclose(det.create_gaussian_shape(1.2), d["g4"], rtol=1e-14)
+    assert np.array_equal(r2.gaussian_shape(0.5), det.create_gaussian_shape(0.5))
+    assert rel_l2(det.resize(d["resize_in"], 30, 45), d["resize_2"]) < 1e-6
+    assert det.resize(d["resize_in"], 60, 90) is d["resize_in"] or np.array_equal(det.resize(d["resize_in"], 60, 90), d["resize_in"])
+    with pytest.raises(ValueError, match="experiment not found in xml file"):
+        shim.Experiment(dict(experimentName="nope", filepath="", overSampling=2, nbExpPoints=1, simulation_type="RayT", expID="x"))
+
+
+def test_public_wave_methods(shim, golden):
+    g = golden("waves")
+    Sample = importlib.import_module("Sample")
+    s = Sample.AnalyticalSample()
+    s.myType, s.myName, s.myMaterials = "membrane", "golden", ["A", "B"]
+    E = float(g["E"])
+    s.delta = [[(E, g["delta"][0]), (40.0, 1.0)], [(E, g["delta"][1])]]
+    s.beta = [[(E, g["beta"][0])], [(40.0, 1.0), (E, g["beta"][1])]]
+    s.myGeometry = g["t"]
+    i_rt, phi_rt, df = s.setWaveRT(g["I"], E, g["phi0"])
+    assert df == 0 and rel_l2(i_rt, g["I_rt"]) < 1e-6 and rel_l2(phi_rt, g["phi_rt"]) < 1e-6
+    w = s.setWave(g["wave0"], E)
+    assert rel_l2(np.abs(w) ** 2, np.abs(g["wave"]) ** 2) < 1e-6
+    s.myGeometry = g["t"][0]
+    with pytest.raises(Exception, match="wrong nb of dim"):
+        s.setWave(g["wave0"], E)
+    e = shim.Experiment.__new__(shim.Experiment)
+    z, M, pix = g["prop1_cfg"]
+    e.exp_dict = {"studyDimensions": np.array(g["wave"].shape), "studyPixelSize": pix}
+    wave = g["wave"]
+    out = e.wavePropagation(wave, z, E, M)
+    assert rel_l2(np.abs(out) ** 2, np.abs(g["prop1"]) ** 2) < TOL
+    assert e.wavePropagation(wave, 0, E, M) is wave          # Experiment.py:233-234
+
+
+def test_main_script_writes_the_output_tree(shim, tmp_path):
+    """main.py flow: membraneThickness/, ref/, sample/, propag/, White_, DF, report (main.py:76-113)."""
+    import argparse
+    from paresis_b200 import workspace
+    from paresis_b200.hostio import imageio
+    sys.path.insert(0, workspace.SHIM_DIR)
+    main = importlib.import_module("main")
+    args = argparse.Namespace(experiment="Small_sphere_mono", results=str(tmp_path / "Results"), oversampling=2, points=2,
+                              model="RayT", format=".tif", seed=3)
+    root = main.run(args)
+    files = sorted(os.path.relpath(os.path.join(dp, f), root) for dp, _, fs in os.walk(root) for f in fs)
+    assert sum(f.startswith("sample/") for f in files) == 2 and sum(f.startswith("ref/") for f in files) == 2
+    assert sum(f.startswith("propag/") for f in files) == 1 and sum(f.startswith("membraneThickness/") for f in files) == 2
+    assert any(f.startswith("White_") for f in files) and "DF.tif" in files
+    img = imageio.read_tiff(os.path.join(root, [f for f in files if f.startswith("sample/")][0]))
+    assert img.shape == (96, 128) and img.dtype == np.float32 and img.mean() > 1000
+    assert np.array_equal(img, np.round(img))            # Poisson counts
+    reports = [f for f in os.listdir(os.path.dirname(os.path.dirname(root))) if f.endswith(".txt")]
+    assert len(reports) == 1
