@@ -1,0 +1,389 @@
+#!/usr/bin/env python3
+"""Benchmark of the PARESIS image-formation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): speckle image-sets/s.  One image-set = everything PARESIS's main.py
+produces for one membrane position (main.py:63-110): a fresh membrane thickness map, the
+sample and reference images (plus propagation and white images at position 0), detector
+blur, binning and Poisson noise included.  Workload = BASELINE.json configs[1]: 2048^2
+oversampled grid, monochromatic 52 keV, 20 membrane positions, ray-tracing refraction model,
+detector PSF 1.2 px + Poisson noise (experiment "B200_2048_mono" of the shipped XML).
+
+One step = one 20-position job.  `value` is measured with all inputs resident in HBM
+(sphere list, sample map); `e2e` runs the same job through the drop-in Python API
+(Experiment.getMyGeometry + computeSampleAndReferenceImages_RT, numpy results on the host,
+membrane map copied back as main.py:99 does).  N > 1: one process per GPU (torchrun), each rank
+its own 20 positions, no data-path collective (positions are independent) -> weak scaling.
+
+`--impl reference` times the CPU oracle port of the same path (oracle/, fp64 numpy + C) on the
+host cores, one process per core, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EXPERIMENT = "B200_2048_mono"
+POSITIONS = 20
+METRIC = "speckle_image_sets_per_s"
+UNIT = "image-sets/s"
+WORKLOAD = "2048^2 grid (detector 1024^2 x os 2), mono 52 keV, 20 membrane positions, RayT, PSF 1.2 px + Poisson"
+
+# algorithmic bytes per study pixel (fp32), SURVEY.md section 8(d) / DESIGN.md "Kernels"
+ALG_BYTES = {
+    "raster_spheres": lambda n, det: 4.0 * n,                 # write the thickness map once
+    "refract_membrane_hop": lambda n, det: 8.0 * n,           # read t_m, write I_bs
+    "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
+    "detect": lambda n, det: 4.0 * n + 4.0 * det,             # read the image, write detector counts (Poisson fused)
+}
+
+
+def config_dict(**extra):
+    c = {"workload": WORKLOAD, "experiment": EXPERIMENT, "positions_per_step": POSITIONS, "grid": 2048,
+         "energies": 1, "model": "RayT"}
+    c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side (oracle port): cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------
+def _oracle_setup():
+    """The same experiment, as scalars for the oracle (values = what the shim derives from the XML)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import paresis_oracle as po
+    from paresis_b200 import workspace
+    from paresis_b200.hostio import tables
+    os.chdir(workspace.make_workspace(tempfile.mkdtemp(prefix="paresis_cpu_")))
+    energy = 52.0
+    cusn, pmma, nylon = (tables.interpolate(m, [energy])[0] for m in ("CuSn", "PMMA", "Nylon"))
+    setup = po.Setup(140.0, 1.6, 3.6, (1024, 1024), 6.0, 2, 30000.0, [(energy, 1.0)], 50.0, 1.2)
+    mdb = {energy: ([cusn[0], pmma[0]], [cusn[1], pmma[1]])}
+    sdb = {energy: ([nylon[0]], [nylon[1]])}
+    sample_t = po.sample_cylinder(700.0, 30.0, setup.study_dims[0], setup.study_dims[1], setup.study_pixel_um)
+    rows = workspace.synthetic_sphere_rows(0, 60000)
+    return po, setup, mdb, sdb, sample_t, rows
+
+
+def _oracle_position(ctx, point, seed):
+    po, setup, mdb, sdb, sample_t, rows = ctx
+    np.random.seed(seed)
+    rng = np.random.RandomState(seed)
+    mem = po.membrane_segmented(rows, 50.0, 3, setup.study_dims[0], setup.study_dims[1], setup.membrane_pixel_um, 6000.0)
+    out = po.compute_rt(setup, mem, mdb, sample_t, sdb, point, poisson=rng.poisson)
+    return float(out[0].sum())
+
+
+_worker_ctx = None
+
+
+def _worker_init():
+    global _worker_ctx
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    _worker_ctx = _oracle_setup()
+    _oracle_position(_worker_ctx, 1, 12345)  # warm caches (FFT plans, page faults)
+
+
+def _worker_run(args):
+    point, seed = args
+    return _oracle_position(_worker_ctx, point, seed)
+
+
+def cpu_baseline_single(positions=(0, 1, 2)):
+    """Scalar port on one core: image-sets/s over a bounded sample of the workload."""
+    ctx = _oracle_setup()
+    _oracle_position(ctx, 1, 999)
+    t0 = time.perf_counter()
+    for p in positions:
+        _oracle_position(ctx, p, 100 + p)
+    dt = time.perf_counter() - t0
+    return {"value": len(positions) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d of the 20 positions (0..%d) at the full 2048^2 grid, fp64 numpy + C oracle, %.1f s"
+                      % (len(positions), len(positions) - 1, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    per_step = workers                      # bounded sample: one position per worker per step
+    with mp.get_context("fork").Pool(workers, initializer=_worker_init) as pool:
+        for w in range(args.warmup):
+            pool.map(_worker_run, [(1, 5000 + w * per_step + i) for i in range(per_step)])
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_worker_run, [(0 if i == 0 else 1, 100 + s * per_step + i) for i in range(per_step)])
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d positions per step (one per worker process, position 0 once per step) at the full 2048^2 grid" % per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(positions_per_step=per_step, note="CPU oracle port of the reference path; the reference "
+                                  "itself is Python/Numba and cannot travel to the GPU box"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run --nproc-per-node N (see module docstring)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from paresis_b200 import _cabi as abi
+    from paresis_b200 import geometry, transfer, workspace
+    ws = workspace.make_workspace(tempfile.mkdtemp(prefix="paresis_bench_r%d_" % rank))
+    workspace.enter(ws)
+    import Experiment as shim
+
+    exp_dict = dict(experimentName=EXPERIMENT, filepath=os.path.join(ws, "out", ""), overSampling=2, nbExpPoints=POSITIONS,
+                    simulation_type="RayT", expID="bench", seed=1234 + rank)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        exp = shim.Experiment(exp_dict)
+    n = int(exp.exp_dict["studyDimensions"][0])
+    det = int(exp.myDetector.det_param["myDimensions"][0])
+    eng = exp._get_engine()
+    mem = exp.myMembrane
+    grains = torch.empty((n, n), device="cuda", dtype=torch.float32)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda", dtype=torch.float32)
+    thresholds = None
+
+    def device_job(step, probe_label=None, events=None):
+        """20 positions with everything resident in HBM; results stay on the device."""
+        nonlocal thresholds
+        np.random.seed((10_000 * rank + step) % (2 ** 32))
+        with abi.on_stream():
+            for point in range(POSITIONS):
+                geom, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, point, mem.myPMMAThickness, out=grains)
+                mem.myGeometry = geom
+                if thresholds is None:
+                    thresholds = list(exp._open_bins(0))
+                    exp.myDetector.det_param["myBinsThersholds"] = []
+                scene = exp._scene(thresholds)
+                probe = None
+                if probe_label in abi.PROBE:
+                    probe = (probe_label, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    events.append(probe[1:])
+                eng.compute_rt(scene, point, want_displacement=False, sequence_base=step * POSITIONS, probe=probe,
+                               want_mean=False)
+        eng.check_flag()
+
+    def api_job(step):
+        """The same job through the reference-facing API: host results, membrane map copied back."""
+        np.random.seed((20_000 * rank + step + 7) % (2 ** 32))
+        geometry._sphere_cache.clear()                      # the sphere list crosses PCIe once per job
+        h0, d0 = transfer.bytes_h2d, transfer.bytes_d2h
+        exp.myDetector.det_param["myBinsThersholds"] = []    # position 0 closes the last bin in place (Experiment.py:429)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for point in range(POSITIONS):
+                mem.myGeometry = []
+                mem.getMyGeometry(exp.exp_dict['studyDimensions'], mem.membranePixelSize, 2, point, POSITIONS)
+                res = exp.computeSampleAndReferenceImages_RT(point)
+                thick = mem.myGeometry[0]                   # main.py:99 saves it
+                assert thick.shape == (n, n) and res[0].shape == (1, det, det)
+        return transfer.bytes_h2d - h0, transfer.bytes_d2h - d0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- per-kernel shares (untimed, after a warm-up): which kernel dominates the step?
+    device_job(-1)
+    torch.cuda.synchronize()
+    shares = profile_kernels(abi, device_job, torch)
+    dominant = max(shares, key=lambda k: shares[k]["ms_per_step"])
+    k_events = []
+
+    # ---- timed region: device-resident job
+    for w in range(args.warmup):
+        device_job(1000 + w)
+    abi.profile_only = dominant if dominant not in abi.PROBE else None
+    abi.profile_events = []
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = abi.launches
+    step_events = []
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()                                       # L2 flush between timed steps (not timed)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); device_job(s, dominant, k_events); e1.record()
+        step_events.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = abi.launches - launches0
+    dev_s = sum(a.elapsed_time(b) for a, b in step_events) * 1e-3
+    k_events = k_events + abi.profile_events
+    abi.profile_only = None
+    k_ms = [a.elapsed_time(b) for a, b in k_events]
+    t = torch.tensor([dev_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t.item())
+    value = world * POSITIONS * args.steps / dev_s
+
+    # ---- e2e through the public API (host results)
+    for w in range(max(1, min(args.warmup, 2))):
+        api_job(3000 + w)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for s in range(args.steps):
+        h2d, d2h = api_job(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * POSITIONS * args.steps / float(t.item())
+    h2d += POSITIONS * 3 * 2 * 8          # the per-layer membrane offsets travel as kernel arguments
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg = ALG_BYTES[dominant](n * n, det * det)
+        avg_ms = float(np.mean(k_ms)) if k_ms else shares[dominant]["ms_per_launch"]
+        achieved = alg / (avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": config_dict(l2="flushed between timed steps (256 MiB write, outside the per-step events)",
+                                  timing="CUDA events per step on the launching stream, max over ranks",
+                                  wall_ms_per_step=wall / args.steps * 1e3),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_timed": len(k_ms)},
+            "kernel_shares": shares,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_kernels(abi, job, torch):
+    """Untimed jobs with CUDA events around one kernel class at a time: ms per step and per launch.
+    (raster: events around the library call; the kernels inside paresis_rt_run: its probe.)"""
+    out = {}
+    abi.profile_only, abi.profile_events = "raster_spheres", []
+    job(-2)
+    torch.cuda.synchronize()
+    v = [a.elapsed_time(b) for a, b in abi.profile_events]
+    abi.profile_only, abi.profile_events = None, []
+    out["raster_spheres"] = {"ms_per_step": float(np.sum(v)), "ms_per_launch": float(np.mean(v)), "launches": len(v)}
+    per_position = {"refract_membrane_hop": 1, "refract_sample_ref_hop": 1, "detect": 2}
+    for k, label in enumerate(abi.PROBE):
+        ev = []
+        job(-3 - k, label, ev)
+        torch.cuda.synchronize()
+        v = [a.elapsed_time(b) for a, b in ev]
+        launches = per_position[label] * len(v) + (3 if label == "detect" else 1 if label == "refract_membrane_hop" else 0)
+        out[label] = {"ms_per_step": float(np.mean(v)) * launches, "ms_per_launch": float(np.mean(v)), "launches": launches}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

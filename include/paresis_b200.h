@@ -41,6 +41,10 @@ typedef struct { float re, im; } paresis_c32;
 
 int paresis_version(void);
 const char* paresis_last_error(void);
+/* Performance knobs, results unaffected.  key 0: deposit mode of the fused refraction kernels
+ * (0 = one REDG per deposit, 2 = warp/register aggregated, default); key 1: source rows per warp
+ * (0 = automatic). */
+int paresis_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------
  * Refraction model (ray tracing)
@@ -102,6 +106,43 @@ int paresis_transmit_rt(const float* intensity_in, const double* phi_in,
                         const double* phase_host, int n_layers,
                         float* intensity_out, double* phi_out, size_t n, paresis_stream stream);
 
+/* Experiment.computeSampleAndReferenceImages_RT for one membrane position in ONE call
+ * (Experiment.py:407-526).  The host prepares, per spectrum energy, the scalars of the three
+ * refraction hops; the library runs the whole launch sequence on `stream`. */
+typedef struct {
+    float intensity_membrane;  /* I0*flux*air*efficiency*plate*exp(-2k sum(beta t)) of the uniform membrane layers (:451-463) */
+    float intensity_propag;    /* I0*flux*air*efficiency*plate: sample-only beam and white field (:490-497) */
+    paresis_layer hop1[PARESIS_MAX_LAYERS];    /* membrane -> object plane, distance d2 (:466) */
+    int n_hop1;
+    paresis_layer hop2[PARESIS_MAX_LAYERS];    /* object -> detector, sample + reference beams, d3 (:473-474) */
+    int n_hop2;
+    paresis_layer propag[PARESIS_MAX_LAYERS];  /* object -> detector without membrane, d3 (:492) */
+    int n_propag;
+    int close_bin;             /* run the detector after this energy (:501) */
+} paresis_rt_energy;
+
+typedef struct {
+    int nx, ny, oversampling, det_x, det_y;
+    int first_point;           /* membrane position 0: propagation and white images too (:488, :510-514) */
+    int n_energies;
+    const paresis_rt_energy* energies_host;
+    float* i_bs;               /* [nx][ny] scratch: intensity in the object plane */
+    float* acc_sample; float* acc_ref; float* acc_propag; float* acc_white;   /* [nx][ny] accumulators */
+    double* means;             /* [n_energies]: mean of acc_ref after each energy (:485-486) */
+    float* detect_work;        /* see paresis_detect_counts; may be NULL for ordinary kernel sizes */
+    const float* src_kernel; int src_half;
+    const float* psf_kernel; int psf_half;
+    int noise; uint64_t seed; uint64_t sequence;   /* Poisson stream: image k of bin b uses sequence + 4b + k */
+    float* out_sample; float* out_ref; float* out_propag; float* out_white;   /* [n_bins][det_x][det_y] */
+    float* dx_pad; float* dy_pad;   /* optional [(nx+30)][(ny+30)]: Dx, Dy of the sample-only beam, last energy (:492) */
+    int* flag;
+    /* optional timing probe: cudaEvent_t pair recorded around one kernel of the first energy / bin
+     * (1 = membrane hop, 2 = sample+reference hop, 3 = detector of the sample image); 0 = off */
+    int probe; void* probe_start; void* probe_end;
+} paresis_rt_job;
+
+int paresis_rt_run(const paresis_rt_job* job_host, paresis_stream stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fresnel model
  * ------------------------------------------------------------------------------------- */
@@ -147,6 +188,17 @@ int paresis_detect(const float* image, int nx, int ny, int oversampling, int det
                    const float* src_kernel, int src_half, const float* psf_kernel, int psf_half,
                    float* work, float* expect_out, paresis_stream stream);
 
+/* Detector.detection in ONE kernel, Poisson draw included (Detector.py:92-118): the production
+ * path.  A thread block stages the window of the oversampled image it needs in shared memory and
+ * runs blur+bin, PSF and (noise != 0) the Philox Poisson draw for pixel p = a*det_y + b on chip.
+ * `work` is only touched for kernels too wide for shared memory (then it must hold
+ * paresis_detect_work_floats floats); it may be NULL otherwise.  out[det_x][det_y]: counts
+ * (noise != 0) or the noise-free expectation. */
+int paresis_detect_counts(const float* image, int nx, int ny, int oversampling, int det_x, int det_y,
+                          const float* src_kernel, int src_half, const float* psf_kernel, int psf_half,
+                          float* work, float* out, int noise, uint64_t seed, uint64_t sequence,
+                          paresis_stream stream);
+
 /* rs.poisson(detectedImage) -- Detector.py:113-115.  Counter-based Philox4x32-10: the draw
  * for pixel p depends only on (seed, sequence, p), so results do not depend on launch shape
  * or on how positions are sharded over GPUs. */
@@ -186,6 +238,8 @@ int paresis_fill(float* dst, float value, size_t n, paresis_stream stream);
 int paresis_axpy(float* dst, const float* src, float scale, size_t n, paresis_stream stream); /* dst += scale*src */
 /* mean of an image (np.mean at Experiment.py:485-486), result to a device double */
 int paresis_mean(const float* src, size_t n, double* out, paresis_stream stream);
+/* *out += scale * sum(src)  (out is NOT cleared) */
+int paresis_sum_scaled(const float* src, size_t n, double scale, double* out, paresis_stream stream);
 
 #ifdef __cplusplus
 }

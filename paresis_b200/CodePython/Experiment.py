@@ -20,7 +20,9 @@ from Source import Source
 from getk import getk
 from refractionFileNumba2 import fastRefraction, fastRefractionDF
 from usefullScripts.getSamplingFactor import is_overSampling_ok
-from paresis_b200 import engine, geometry, host_api
+import torch
+
+from paresis_b200 import engine, geometry, host_api, transfer
 from paresis_b200.hostio import xmlparams
 
 
@@ -244,9 +246,15 @@ class Experiment:
         return self._engine
 
     def _finish(self, res):
+        """Device images -> the float64 [nbins, dimX, dimY] arrays the reference returns; images that were
+        not computed (propagation / white beyond point 0) are zeros, as upstream (Experiment.py:433-434)."""
         num, den = res["mean_energy"]
         self.exp_dict['meanEnergy'] = (self.exp_dict['meanEnergy'] + num) / den      # Experiment.py:486, :523
-        return [res[k].cpu().numpy().astype(np.float64) for k in engine.IMAGES]
+        host = transfer.fetch(res["_stack"], torch.float64)       # one cast + one PCIe copy for all images
+        out = [host[i] for i in range(host.shape[0])]
+        while len(out) < 4:
+            out.append(np.zeros(out[0].shape))
+        return out
 
     def computeSampleAndReferenceImages_Fresnel(self, pointNum):
         """All images of one membrane position with the Fresnel propagator (Experiment.py:279-405).
@@ -284,8 +292,8 @@ class Experiment:
             raise Exception(str(exc))
         out = self._finish(res)
         if want_d:
-            self.Dxreal = eng.dx_pad.cpu().numpy().astype(np.float64)
-            self.Dyreal = eng.dy_pad.cpu().numpy().astype(np.float64)
+            self.Dxreal = transfer.fetch(eng.dx_pad, torch.float64)
+            self.Dyreal = transfer.fetch(eng.dy_pad, torch.float64)
         n = self.exp_dict['studyDimensions']
         self.darkFieldPropag = np.zeros((n[0], n[1]))
         print("Mean detected energy in reference image", self.exp_dict['meanEnergy'])

@@ -34,4 +34,4 @@ def getMembraneSegmentedFromFile(sample, dimX, dimY, pixSize, pointNum, supportT
         geometry: [grains, support] thickness maps in metres (device-resident, ndarray-like).
         parameters_dic (dict): values written to the run report.
     """
-    return geometry.membrane_segmented(sample, dimX, dimY, pixSize, pointNum, supportThickness)
+    return geometry.membrane_segmented(sample, dimX, dimY, pixSize, pointNum, supportThickness, prefetch=True)

@@ -20,11 +20,12 @@ REFRACTION_MARGIN = 15   # refractionFileNumba2.py:50
 REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
 
 EXPORTS = (
-    "paresis_version", "paresis_last_error", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
+    "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
     "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_detect_work_floats", "paresis_detect",
+    "paresis_detect_counts",
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
-    "paresis_fill", "paresis_axpy", "paresis_mean",
+    "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run",
 )
 
 
@@ -35,6 +36,29 @@ class ParesisError(RuntimeError):
 class Layer(ctypes.Structure):
     _fields_ = [("thickness", ctypes.c_void_p), ("grad_obj", ctypes.c_float), ("grad_ref", ctypes.c_float),
                 ("atten", ctypes.c_float)]
+
+
+class RtEnergy(ctypes.Structure):
+    _fields_ = [("intensity_membrane", ctypes.c_float), ("intensity_propag", ctypes.c_float),
+                ("hop1", Layer * MAX_LAYERS), ("n_hop1", ctypes.c_int),
+                ("hop2", Layer * MAX_LAYERS), ("n_hop2", ctypes.c_int),
+                ("propag", Layer * MAX_LAYERS), ("n_propag", ctypes.c_int),
+                ("close_bin", ctypes.c_int)]
+
+
+class RtJob(ctypes.Structure):
+    _fields_ = [("nx", ctypes.c_int), ("ny", ctypes.c_int), ("oversampling", ctypes.c_int), ("det_x", ctypes.c_int),
+                ("det_y", ctypes.c_int), ("first_point", ctypes.c_int), ("n_energies", ctypes.c_int),
+                ("energies_host", ctypes.POINTER(RtEnergy)),
+                ("i_bs", ctypes.c_void_p), ("acc_sample", ctypes.c_void_p), ("acc_ref", ctypes.c_void_p),
+                ("acc_propag", ctypes.c_void_p), ("acc_white", ctypes.c_void_p), ("means", ctypes.c_void_p),
+                ("detect_work", ctypes.c_void_p), ("src_kernel", ctypes.c_void_p), ("src_half", ctypes.c_int),
+                ("psf_kernel", ctypes.c_void_p), ("psf_half", ctypes.c_int), ("noise", ctypes.c_int),
+                ("seed", ctypes.c_uint64), ("sequence", ctypes.c_uint64),
+                ("out_sample", ctypes.c_void_p), ("out_ref", ctypes.c_void_p), ("out_propag", ctypes.c_void_p),
+                ("out_white", ctypes.c_void_p), ("dx_pad", ctypes.c_void_p), ("dy_pad", ctypes.c_void_p),
+                ("flag", ctypes.c_void_p), ("probe", ctypes.c_int), ("probe_start", ctypes.c_void_p),
+                ("probe_end", ctypes.c_void_p)]
 
 
 class C32(ctypes.Structure):
@@ -54,6 +78,7 @@ def _load():
     lib.paresis_version.restype = ci
     lib.paresis_last_error.restype = ctypes.c_char_p
     sig = {
+        "paresis_set_tuning": [ci, ci],
         "paresis_splat": [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp],
         "paresis_refract_phi": [vp, vp, vp, vp, vp, ci, ci, ci, cd, cd, cd, cd, cd, vp, vp],
         "paresis_refract_layers": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, vp, vp, ci, ci, ci, vp, vp],
@@ -63,6 +88,7 @@ def _load():
         "paresis_fresnel_plan_destroy": [vp],
         "paresis_fresnel_propagate": [vp, vp, vp, vp, C32, vp, vp, vp],
         "paresis_detect": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, vp],
+        "paresis_detect_counts": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, ci, u64, u64, vp],
         "paresis_poisson": [vp, vp, sz, u64, u64, vp],
         "paresis_bin_sum": [vp, ci, ci, ci, ci, vp, vp],
         "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp],
@@ -71,6 +97,8 @@ def _load():
         "paresis_fill": [vp, cf, sz, vp],
         "paresis_axpy": [vp, vp, cf, sz, vp],
         "paresis_mean": [vp, sz, vp, vp],
+        "paresis_sum_scaled": [vp, sz, cd, vp, vp],
+        "paresis_rt_run": [ctypes.POINTER(RtJob), vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -94,8 +122,44 @@ def _check(rc, what):
         raise ParesisError("%s failed (%d): %s" % (what, rc, lib.paresis_last_error().decode()))
 
 
+_stream_override = None
+
+
 def _stream():
+    if _stream_override is not None:
+        return _stream_override
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class on_stream:
+    """Resolve torch's current stream once for a batch of library calls (the lookup costs ~20 us)."""
+
+    def __enter__(self):
+        global _stream_override
+        self.prev = _stream_override
+        _stream_override = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def __exit__(self, *exc):
+        global _stream_override
+        _stream_override = self.prev
+
+
+# probe kinds of paresis_rt_run
+PROBE = {"refract_membrane_hop": 1, "refract_sample_ref_hop": 2, "detect": 3}
+
+
+def rt_run(job, launches_in_job, probe=None):
+    """paresis_rt_run; `probe` = (kind label, start Event, end Event) records one kernel of the call."""
+    if probe is not None:
+        label, e0, e1 = probe
+        for e in (e0, e1):
+            if not e.cuda_event:
+                e.record()          # materialise the underlying cudaEvent_t
+        job.probe, job.probe_start, job.probe_end = PROBE[label], e0.cuda_event, e1.cuda_event
+    else:
+        job.probe = 0
+    _check(lib.paresis_rt_run(ctypes.byref(job), _stream()), "paresis_rt_run")
+    _count(launches_in_job)
 
 
 def _ptr(t, dtype=None):
@@ -111,6 +175,28 @@ def _ptr(t, dtype=None):
 def _count(n=1):
     global launches
     launches += n
+
+
+# Optional CUDA-event timing of library calls (used by bench.py): None = off, "*" = every call
+# (events stored as (label, start, end)), or one label (stored as (start, end)).
+profile_only = None
+profile_events = []
+
+
+def _timed(label, call):
+    if profile_only is None or (profile_only != "*" and profile_only != label):
+        return call()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = call()
+    e1.record()
+    profile_events.append((label, e0, e1) if profile_only == "*" else (e0, e1))
+    return rc
+
+
+def set_tuning(key, value):
+    _check(lib.paresis_set_tuning(int(key), int(value)), "paresis_set_tuning")
 
 
 def splat(intensity, dx, dy, out, margin=0, variant=2, flag=None):
@@ -141,10 +227,11 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
         arr[k].grad_obj, arr[k].grad_ref, arr[k].atten = float(go), float(gr), float(at)
         _ptr(t, torch.float32)
     nx, ny = out_obj.shape
-    _check(lib.paresis_refract_layers(_ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n,
-                                      _ptr(out_obj, torch.float32), _ptr(out_ref, torch.float32),
-                                      _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
-                                      _ptr(flag, torch.int32), _stream()), "paresis_refract_layers")
+    label = "refract_sample_ref_hop" if out_ref is not None else "refract_membrane_hop"
+    _check(_timed(label, lambda: lib.paresis_refract_layers(
+        _ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n, _ptr(out_obj, torch.float32),
+        _ptr(out_ref, torch.float32), _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
+        _ptr(flag, torch.int32), _stream())), "paresis_refract_layers")
     _count()
 
 
@@ -213,15 +300,28 @@ def detect(image, oversampling, det_x, det_y, src_kernel, psf_kernel, work, expe
     nx, ny = image.shape
     sh = 0 if src_kernel is None else (src_kernel.numel() - 1) // 2
     ph = 0 if psf_kernel is None else (psf_kernel.numel() - 1) // 2
-    _check(lib.paresis_detect(_ptr(image, torch.float32), nx, ny, oversampling, det_x, det_y,
-                              _ptr(src_kernel, torch.float32), sh, _ptr(psf_kernel, torch.float32), ph,
-                              _ptr(work, torch.float32), _ptr(expect_out, torch.float32), _stream()), "paresis_detect")
+    _check(_timed("detect", lambda: lib.paresis_detect(
+        _ptr(image, torch.float32), nx, ny, oversampling, det_x, det_y, _ptr(src_kernel, torch.float32), sh,
+        _ptr(psf_kernel, torch.float32), ph, _ptr(work, torch.float32), _ptr(expect_out, torch.float32), _stream())),
+        "paresis_detect")
     _count(4 if ph else 3)
 
 
+def detect_counts(image, oversampling, det_x, det_y, src_kernel, psf_kernel, work, out, noise, seed=0, sequence=0):
+    nx, ny = image.shape
+    sh = 0 if src_kernel is None else (src_kernel.numel() - 1) // 2
+    ph = 0 if psf_kernel is None else (psf_kernel.numel() - 1) // 2
+    _check(_timed("detect", lambda: lib.paresis_detect_counts(
+        _ptr(image, torch.float32), nx, ny, oversampling, det_x, det_y, _ptr(src_kernel, torch.float32), sh,
+        _ptr(psf_kernel, torch.float32), ph, _ptr(work, torch.float32), _ptr(out, torch.float32), 1 if noise else 0,
+        int(seed) & (2 ** 64 - 1), int(sequence) & (2 ** 64 - 1), _stream())), "paresis_detect_counts")
+    _count()
+
+
 def poisson(expect, counts, seed, sequence):
-    _check(lib.paresis_poisson(_ptr(expect, torch.float32), _ptr(counts, torch.float32), expect.numel(),
-                               int(seed) & (2 ** 64 - 1), int(sequence) & (2 ** 64 - 1), _stream()), "paresis_poisson")
+    _check(_timed("poisson", lambda: lib.paresis_poisson(
+        _ptr(expect, torch.float32), _ptr(counts, torch.float32), expect.numel(), int(seed) & (2 ** 64 - 1),
+        int(sequence) & (2 ** 64 - 1), _stream())), "paresis_poisson")
     _count()
 
 
@@ -234,10 +334,9 @@ def bin_sum(image, size_x, size_y, out):
 
 def raster_spheres(spheres, pix_um, offsets, dim_x, dim_y, margin, out):
     offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(-1, 2))
-    _check(lib.paresis_raster_spheres(_ptr(spheres, torch.float64), spheres.shape[0], float(pix_um),
-                                      offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), offs.shape[0],
-                                      dim_x, dim_y, margin, _ptr(out, torch.float32), _stream()),
-           "paresis_raster_spheres")
+    _check(_timed("raster_spheres", lambda: lib.paresis_raster_spheres(
+        _ptr(spheres, torch.float64), spheres.shape[0], float(pix_um), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        offs.shape[0], dim_x, dim_y, margin, _ptr(out, torch.float32), _stream())), "paresis_raster_spheres")
     _count()
 
 

@@ -159,6 +159,13 @@ extern "C" int paresis_axpy(float* dst, const float* src, float scale, size_t n,
     return PARESIS_OK;
 }
 
+extern "C" int paresis_sum_scaled(const float* src, size_t n, double scale, double* out, paresis_stream stream) {
+    if (!src || !out || n == 0) { set_last_error("paresis_sum_scaled: bad arguments"); return PARESIS_ERR_ARG; }
+    sum_kernel<<<ew_blocks(n, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(src, n, scale, out);
+    PARESIS_LAUNCH_CHECK("sum_kernel");
+    return PARESIS_OK;
+}
+
 extern "C" int paresis_mean(const float* src, size_t n, double* out, paresis_stream stream) {
     if (!src || !out || n == 0) { set_last_error("paresis_mean: bad arguments"); return PARESIS_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;

@@ -28,26 +28,28 @@ splat_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const fl
     const int i0 = blockIdx.y * rows;
     const int i1 = min(i0 + rows, f.nx);
     const bool live = j < f.ny;
+    const bool full_warp = __all_sync(FULL_MASK, live);
     Splatter<MODE> sp;
     sp.init(out, f.ny, flag);
     constexpr int U = 4;
+    const size_t col = live ? j : 0;
     for (int ib = i0; ib < i1; ib += U) {
         float v[U], dx[U], dy[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = ib + u;
-            const bool on = live && i < i1;
-            const size_t p = (size_t)i * f.ny + j;
-            v[u] = on ? ld_stream(I + p) : 0.f;
-            dx[u] = on ? ld_stream(Dx + p) : 0.f;
-            dy[u] = on ? ld_stream(Dy + p) : 0.f;
+            const int i = min(ib + u, i1 - 1);
+            const size_t p = (size_t)i * f.ny + col;
+            v[u] = __ldg(I + p);
+            dx[u] = __ldg(Dx + p);
+            dy[u] = __ldg(Dy + p);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = ib + u;
             if (i < i1) {  // warp-uniform
-                Ray q = live ? make_ray(i, j, v[u], dx[u], dy[u], f) : empty_ray();
-                sp.put(q);
+                const FastRay q = fast_ray(i, j, v[u], dx[u], dy[u], f.nx, f.ny);
+                if (full_warp && __all_sync(FULL_MASK, q.simple)) sp.put_simple(q);
+                else sp.put(live ? make_ray(i, j, v[u], dx[u], dy[u], f) : empty_ray());
             }
         }
     }
@@ -85,7 +87,7 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
     if (by) dy = 0.f;
 }
 
-template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT, bool WRITE_D>
+template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT, bool WRITE_D, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 refract_kernel(const RefractArgs<T> a) {
     const Frame f = a.f;
@@ -95,31 +97,44 @@ refract_kernel(const RefractArgs<T> a) {
     const int i1 = min(i0 + a.rows, f.nx);
     const bool live = j < f.ny;
     const int jc = live ? j : f.ny - 1;  // dead lanes read a valid address, contribute nothing
+    // the strip is "inner" when no lane sits on the first / last image column and every lane is live
+    const bool inner_cols = __all_sync(FULL_MASK, live && j > 0 && j < f.ny - 1);
 
     // rolling rows: up = row i-1, mid = row i, dn = row i+1 (difference first, scale after)
     T up[NM], mid[NM], dn[NM];
+    const T* row[NM];    // points at (row i+2, column jc): the next row to fetch
+    const T* halo[NM];   // points at (row i, column jc -+ 1) for the first / last lane of the strip
+    const bool edge_lane = lane == 0 || lane == 31;
+    const int jh = min(max(lane == 0 ? jc - 1 : jc + 1, 0), f.ny - 1);
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-        const T* t = a.map[m];
-        mid[m] = ld_stream(t + (size_t)i0 * f.ny + jc);
-        up[m] = i0 > 0 ? ld_stream(t + (size_t)(i0 - 1) * f.ny + jc) : mid[m];
-        dn[m] = i0 + 1 < f.nx ? ld_stream(t + (size_t)(i0 + 1) * f.ny + jc) : mid[m];
+        const T* t = a.map[m] + jc;
+        mid[m] = __ldg(t + (size_t)i0 * f.ny);
+        up[m] = i0 > 0 ? __ldg(t + (size_t)(i0 - 1) * f.ny) : mid[m];
+        dn[m] = i0 + 1 < f.nx ? __ldg(t + (size_t)(i0 + 1) * f.ny) : mid[m];
+        row[m] = t + (size_t)(i0 + 2) * f.ny;
+        halo[m] = a.map[m] + (size_t)i0 * f.ny + jh;
     }
-    float vin = HAS_I ? ld_stream(a.I_in + (size_t)i0 * f.ny + jc) : a.I_uniform;
+    const float* irow = HAS_I ? a.I_in + (size_t)i0 * f.ny + jc : nullptr;
+    float vin = HAS_I ? __ldg(irow) : a.I_uniform;
 
-    Splatter<2> sp_obj, sp_ref;
+    Splatter<MODE> sp_obj, sp_ref;
     sp_obj.init(a.out_obj, f.ny, a.flag);
     if (DUAL) sp_ref.init(a.out_ref, f.ny, a.flag);
 
     for (int i = i0; i < i1; ++i) {
-        // prefetch the row after next and the next intensity before touching this row
+        // fetch the row after next and the next intensity before touching this row
         T nxt[NM];
         const bool more = i + 2 < f.nx && i + 1 < i1;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) nxt[m] = more ? ld_stream(a.map[m] + (size_t)(i + 2) * f.ny + jc) : dn[m];
+        for (int m = 0; m < NM; ++m) {
+            nxt[m] = more ? __ldg(row[m]) : dn[m];
+            row[m] += f.ny;
+        }
         float vnext = vin;
-        if (HAS_I && i + 1 < i1) vnext = ld_stream(a.I_in + (size_t)(i + 1) * f.ny + jc);
+        if (HAS_I && i + 1 < i1) { irow += f.ny; vnext = __ldg(irow); }
 
+        const bool inner = inner_cols && i > 0 && i < f.nx - 1;   // warp-uniform
         float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
@@ -127,16 +142,24 @@ refract_kernel(const RefractArgs<T> a) {
             // neighbours along the row come from the adjacent lanes; the strip edges load them
             T lf = __shfl_up_sync(FULL_MASK, mid[m], 1);
             T rt = __shfl_down_sync(FULL_MASK, mid[m], 1);
-            if (lane == 0 && jc > 0) lf = ld_stream(t + (size_t)i * f.ny + jc - 1);
-            if (lane == 31 && jc + 1 < f.ny) rt = ld_stream(t + (size_t)i * f.ny + jc + 1);
-            // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
+            if (edge_lane) {   // one predicated load serves both ends of the strip
+                const T h = __ldg(halo[m]);
+                if (lane == 0) lf = h; else rt = h;
+            }
+            halo[m] += f.ny;
             T gy, gx;
-            if (jc == 0) gy = -(T)3 * mid[m] + (T)4 * rt - ld_stream(t + (size_t)i * f.ny + 2);
-            else if (jc == f.ny - 1) gy = (T)3 * mid[m] - (T)4 * lf + ld_stream(t + (size_t)i * f.ny + f.ny - 3);
-            else gy = rt - lf;
-            if (i == 0) gx = -(T)3 * mid[m] + (T)4 * dn[m] - ld_stream(t + (size_t)2 * f.ny + jc);
-            else if (i == f.nx - 1) gx = (T)3 * mid[m] - (T)4 * up[m] + ld_stream(t + (size_t)(f.nx - 3) * f.ny + jc);
-            else gx = dn[m] - up[m];
+            if (inner) {
+                gy = rt - lf;
+                gx = dn[m] - up[m];
+            } else {
+                // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
+                if (jc == 0) gy = -(T)3 * mid[m] + (T)4 * rt - __ldg(t + (size_t)i * f.ny + 2);
+                else if (jc == f.ny - 1) gy = (T)3 * mid[m] - (T)4 * lf + __ldg(t + (size_t)i * f.ny + f.ny - 3);
+                else gy = rt - lf;
+                if (i == 0) gx = -(T)3 * mid[m] + (T)4 * dn[m] - __ldg(t + (size_t)2 * f.ny + jc);
+                else if (i == f.nx - 1) gx = (T)3 * mid[m] - (T)4 * up[m] + __ldg(t + (size_t)(f.nx - 3) * f.ny + jc);
+                else gx = dn[m] - up[m];
+            }
             const float gxf = (float)gx, gyf = (float)gy;
             dxo = fmaf(a.g_obj[m], gxf, dxo);
             dyo = fmaf(a.g_obj[m], gyf, dyo);
@@ -155,9 +178,16 @@ refract_kernel(const RefractArgs<T> a) {
             a.dx_pad[pp] = dxo;
             a.dy_pad[pp] = dyo;
         }
-        sp_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
-        if (DUAL) sp_ref.put(live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray());
-
+        {
+            const FastRay q = fast_ray(i, j, vo, dxo, dyo, f.nx, f.ny);
+            if (inner_cols && __all_sync(FULL_MASK, q.simple)) sp_obj.put_simple(q);
+            else sp_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
+        }
+        if (DUAL) {
+            const FastRay q = fast_ray(i, j, vr, dxr, dyr, f.nx, f.ny);
+            if (inner_cols && __all_sync(FULL_MASK, q.simple)) sp_ref.put_simple(q);
+            else sp_ref.put(live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray());
+        }
 #pragma unroll
         for (int m = 0; m < NM; ++m) { up[m] = mid[m]; mid[m] = dn[m]; dn[m] = nxt[m]; }
         vin = vnext;
@@ -166,6 +196,10 @@ refract_kernel(const RefractArgs<T> a) {
     if (DUAL) sp_ref.finish();
 }
 
+// Tuning knobs (paresis_set_tuning): deposit mode of the fused kernels, rows per warp.
+static int g_fused_mode = 2;
+static int g_rows_override = 0;
+
 // rows per warp: enough blocks for ~2 waves of 148 SMs x 8 resident blocks, few halo re-reads
 static int pick_rows(int nx, int ny) {
     const int strips = div_up(ny, BLOCK_THREADS);
@@ -173,6 +207,7 @@ static int pick_rows(int nx, int ny) {
     int rows = (int)((long)nx * strips / target_blocks);
     if (rows < 8) rows = 8;
     if (rows > 64) rows = 64;
+    if (g_rows_override > 0) rows = g_rows_override;
     return rows;
 }
 
@@ -187,8 +222,9 @@ static int check_frame(int nx, int ny, int margin) {
 template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT>
 static int launch_refract(const RefractArgs<T>& a, bool write_d, cudaStream_t s) {
     dim3 grid(div_up(a.f.ny, BLOCK_THREADS), div_up(a.f.nx, a.rows));
-    if (write_d) refract_kernel<T, NM, DUAL, HAS_I, ATT, true><<<grid, BLOCK_THREADS, 0, s>>>(a);
-    else refract_kernel<T, NM, DUAL, HAS_I, ATT, false><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    if (write_d) refract_kernel<T, NM, DUAL, HAS_I, ATT, true, 2><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    else if (g_fused_mode == 0) refract_kernel<T, NM, DUAL, HAS_I, ATT, false, 0><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    else refract_kernel<T, NM, DUAL, HAS_I, ATT, false, 2><<<grid, BLOCK_THREADS, 0, s>>>(a);
     PARESIS_LAUNCH_CHECK("refract_kernel");
     return PARESIS_OK;
 }
@@ -206,6 +242,14 @@ static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
 }  // namespace paresis
 
 using namespace paresis;
+
+extern "C" int paresis_set_tuning(int key, int value) {
+    switch (key) {
+        case 0: g_fused_mode = value == 0 ? 0 : 2; return PARESIS_OK;
+        case 1: g_rows_override = value; return PARESIS_OK;
+        default: set_last_error("paresis_set_tuning: unknown key %d", key); return PARESIS_ERR_ARG;
+    }
+}
 
 extern "C" int paresis_splat(const float* intensity, const float* dx, const float* dy, float* out,
                              int nx, int ny, int margin, int variant, int* flag, paresis_stream stream) {

@@ -78,6 +78,30 @@ __device__ __forceinline__ Ray make_ray(int i, int j, float v, float dx, float d
     return q;
 }
 
+// The same ray by plain floor arithmetic: r = i + floor(dx), weights (1-f, f).  Numerically the
+// reference's map for every displacement (|D| <= 1 included, see DESIGN.md "Splat semantics"); what
+// it cannot express is the loop-frame edge rule of :235-262, so it is only used when all four cells
+// lie strictly inside the image (`simple`), where that rule never fires.  Anything else goes
+// through make_ray().
+struct FastRay {
+    int key;               // r * ny + c of the lower cell
+    float w0, w1, w2, w3;  // (r,c) (r,c+1) (r+1,c) (r+1,c+1)
+    bool simple;
+};
+
+__device__ __forceinline__ FastRay fast_ray(int i, int j, float v, float dx, float dy, int nx, int ny) {
+    FastRay q;
+    const float flx = floorf(dx), fly = floorf(dy);
+    const float fx = dx - flx, fy = dy - fly;
+    const int r = i + __float2int_rd(dx), c = j + __float2int_rd(dy);   // saturating; wrap-around fails `simple`
+    q.simple = ((unsigned)r < (unsigned)(nx - 1)) & ((unsigned)c < (unsigned)(ny - 1));
+    const float v1 = v * fx, v0 = v - v1;
+    q.w1 = v0 * fy; q.w0 = v0 - q.w1;
+    q.w3 = v1 * fy; q.w2 = v1 - q.w3;
+    q.key = r * ny + c;
+    return q;
+}
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int NO_KEY = -(1 << 30);
 
@@ -90,11 +114,13 @@ struct Splatter {
     int carry_key;
     float carry_val;
     int* flag;
+    bool bad;   // a non-finite deposit was seen; published once, in finish()
 
     __device__ __forceinline__ void init(float* out_, int ny_, int* flag_) {
         out = out_; ny = ny_; flag = flag_;
         lane = threadIdx.x & 31;
         carry_key = NO_KEY; carry_val = 0.f;
+        bad = false;
     }
 
     __device__ __forceinline__ void cells(const Ray& q) {
@@ -108,7 +134,7 @@ struct Splatter {
     __device__ __forceinline__ void put(const Ray& q) {
         if (q.ok) {
             const float s = (q.w[0] + q.w[1]) + (q.w[2] + q.w[3]);
-            if (!(fabsf(s) <= 3.0e38f) && flag) atomicOr(flag, FLAG_NONFINITE);
+            bad |= !(fabsf(s) <= 3.0e38f);
         }
         if (MODE == 0) {
             cells(q);
@@ -144,8 +170,44 @@ struct Splatter {
         }
     }
 
+    // Fast path: every lane of the warp holds a `simple` ray (all four cells inside the image).
+    __device__ __forceinline__ void put_simple(const FastRay& q) {
+        bad |= !(fabsf(q.w0 + q.w3) <= 3.0e38f);
+        if (MODE == 0) {
+            float* p = out + q.key;
+            if (q.w0 != 0.f) red_add(p, q.w0);
+            if (q.w1 != 0.f) red_add(p + 1, q.w1);
+            if (q.w2 != 0.f) red_add(p + ny, q.w2);
+            if (q.w3 != 0.f) red_add(p + ny + 1, q.w3);
+            return;
+        }
+        const int kprev = __shfl_up_sync(FULL_MASK, q.key, 1);
+        const float w1p = __shfl_up_sync(FULL_MASK, q.w1, 1);
+        const float w3p = __shfl_up_sync(FULL_MASK, q.w3, 1);
+        const bool absorb = lane > 0 && q.key == kprev + 1;
+        const unsigned m = __ballot_sync(FULL_MASK, absorb);
+        const bool given = ((m >> lane) >> 1) & 1u;
+        float top = q.w0, bot = q.w2;
+        if (absorb) { top += w1p; bot += w3p; }
+        float* p = out + q.key;
+        if (MODE == 2) {
+            if (carry_key == q.key) top += carry_val;
+            else if (carry_key != NO_KEY) red_add(out + carry_key, carry_val);
+            if (bot != 0.f) { carry_key = q.key + ny; carry_val = bot; }
+            else carry_key = NO_KEY;
+        } else if (bot != 0.f) {
+            red_add(p + ny, bot);
+        }
+        if (top != 0.f) red_add(p, top);
+        if (!given) {
+            if (q.w1 != 0.f) red_add(p + 1, q.w1);
+            if (q.w3 != 0.f) red_add(p + ny + 1, q.w3);
+        }
+    }
+
     __device__ __forceinline__ void finish() {
         if (MODE == 2 && carry_key != NO_KEY) { red_add(out + carry_key, carry_val); carry_key = NO_KEY; }
+        if (bad && flag) atomicOr(flag, FLAG_NONFINITE);
     }
 };
 

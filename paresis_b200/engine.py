@@ -115,11 +115,7 @@ class ImageFormation:
         """Detector.detection (Detector.py:79-119): device image -> ``out`` (device, detector dims)."""
         src = self._gauss(fwhm / 2.355) if fwhm != 0 else None
         psf = self._gauss(psf_sigma) if psf_sigma != 0 else None
-        if self.poisson:
-            abi.detect(image, self.os, self.det_x, self.det_y, src, psf, self.work, self.expect)
-            abi.poisson(self.expect, out, self.seed, sequence)
-        else:
-            abi.detect(image, self.os, self.det_x, self.det_y, src, psf, self.work, out)
+        abi.detect_counts(image, self.os, self.det_x, self.det_y, src, psf, self.work, out, self.poisson, self.seed, sequence)
 
     def check_flag(self):
         """The reference's NaN / 'insane values' guard (refractionFileNumba2.py:81-82), checked lazily."""
@@ -140,9 +136,100 @@ class ImageFormation:
                 ud += d * L.uniform
         return maps, ub, ud
 
-    def _new_outputs(self, nbins):
-        return {k: torch.zeros((nbins, self.det_x, self.det_y), device=self.device, dtype=torch.float32) for k in IMAGES}
+    def _new_outputs(self, nbins, first):
+        """Detector images of one position, stacked [image][bin][x][y] in ONE device buffer
+        (sample, reference; + propag, white at position 0) so they cross PCIe as one copy."""
+        count = 4 if first else 2
+        stack = torch.empty((count, nbins, self.det_x, self.det_y), device=self.device, dtype=torch.float32)
+        out = {k: stack[i] for i, k in enumerate(IMAGES[:count])}
+        out["_stack"] = stack
+        return out
 
+    def _mean_energy(self, energies, bin_starts):
+        """Experiment.py:485-486, :523 from the running means of the reference accumulator."""
+        r = self.means[:len(energies)].cpu().numpy()
+        per = r.copy()
+        for i in range(1, len(per)):
+            if i not in bin_starts:
+                per[i] = r[i] - r[i - 1]
+        return float(np.dot(per, energies)), float(per.sum())
+
+    # ------------------------------------------------------------------ ray tracing
+    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True):
+        """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526) as one library
+        call (paresis_rt_run).
+
+        Returns a dict of device tensors [nbins, det_x, det_y]: sample, reference (+ propag, white
+        at position 0; absent keys are all-zero images), plus ``mean_energy`` = (sum E*mean,
+        sum mean) of Experiment.py:485-486."""
+        s = scene
+        first = point_num == 0
+        nbins = len(s.thresholds)
+        n_e = len(s.spectrum)
+        out = self._new_outputs(nbins, first)
+        if n_e > self.means.numel():
+            self.means = torch.zeros(n_e, device=self.device, dtype=torch.float64)
+        wd = first and want_displacement
+        if wd and self.dx_pad is None:
+            self.dx_pad = torch.empty((self.nx + 30, self.ny + 30), device=self.device, dtype=torch.float32)
+            self.dy_pad = torch.empty_like(self.dx_pad)
+        g2 = hm.refraction_gradient_scale(s.d2, s.magnification, s.study_pixel_um)
+        g3 = hm.refraction_gradient_scale(s.d3, s.magnification, s.study_pixel_um)
+        energies = (abi.RtEnergy * n_e)()
+        ibin, bin_starts, keep = 0, {0}, []
+        for ie, (energy, flux) in enumerate(s.spectrum):
+            k = hm.wavenumber(energy * 1000)
+            i0 = s.mean_shot_count / s.os ** 2 * flux * s.common_factor(energy)      # :438, :451-459
+            plate = s.plate_factor(energy)
+            mem_maps, mem_ub, _ = self._split(s.membrane, energy)
+            smp_maps, smp_ub, _ = self._split(s.sample, energy)
+            if smp_ub != 0.0 or not mem_maps or not smp_maps or len(mem_maps) + len(smp_maps) > abi.MAX_LAYERS:
+                raise NotImplementedError("scene needs 1+ membrane maps, sample maps only, at most %d maps per hop"
+                                          % abi.MAX_LAYERS)
+            en = energies[ie]
+            # uniform layers and the plate only scale the beam (:463, :478-480)
+            en.intensity_membrane = i0 * np.exp(-2 * k * mem_ub) * plate
+            en.intensity_propag = i0 * plate
+            hop1 = [(t, d * g2, 0.0, 2 * k * b) for t, d, b in mem_maps]
+            hop2 = [(t, d * g3, d * g3, 0.0) for t, d, b in mem_maps] + [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps]
+            prop = [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps]
+            for dst, src in ((en.hop1, hop1), (en.hop2, hop2), (en.propag, prop)):
+                for m, (t, go, gr, at) in enumerate(src):
+                    dst[m].thickness, dst[m].grad_obj, dst[m].grad_ref, dst[m].atten = t.data_ptr(), go, gr, at
+                    keep.append(t)
+            en.n_hop1, en.n_hop2, en.n_propag = len(hop1), len(hop2), len(prop)
+            en.close_bin = 1 if energy > s.thresholds[ibin] - s.energy_sampling / 2 else 0    # :501
+            if en.close_bin:
+                ibin += 1
+                if ie + 1 < n_e:
+                    bin_starts.add(ie + 1)
+        fwhm = s.effective_source_fwhm()
+        src = self._gauss(fwhm / 2.355) if fwhm != 0 else None
+        psf = self._gauss(s.psf_sigma) if s.psf_sigma != 0 else None
+        job = abi.RtJob()
+        job.nx, job.ny, job.oversampling, job.det_x, job.det_y = self.nx, self.ny, self.os, self.det_x, self.det_y
+        job.first_point, job.n_energies, job.energies_host = int(first), n_e, energies
+        job.i_bs = self.i_bs.data_ptr()
+        job.acc_sample, job.acc_ref = self.acc["sample"].data_ptr(), self.acc["reference"].data_ptr()
+        job.acc_propag, job.acc_white = self.acc["propag"].data_ptr(), self.acc["white"].data_ptr()
+        job.means, job.detect_work = self.means.data_ptr(), self.work.data_ptr()
+        job.src_kernel, job.src_half = (src.data_ptr(), (src.numel() - 1) // 2) if src is not None else (None, 0)
+        job.psf_kernel, job.psf_half = (psf.data_ptr(), (psf.numel() - 1) // 2) if psf is not None else (None, 0)
+        job.noise, job.seed, job.sequence = int(self.poisson), self.seed, ((sequence_base + point_num) << 16)
+        job.out_sample, job.out_ref = out["sample"].data_ptr(), out["reference"].data_ptr()
+        if first:
+            job.out_propag, job.out_white = out["propag"].data_ptr(), out["white"].data_ptr()
+        if wd:
+            job.dx_pad, job.dy_pad = self.dx_pad.data_ptr(), self.dy_pad.data_ptr()
+        job.flag = self.flag.data_ptr()
+        launches = n_e * (4 if first else 3) + ibin * (5 if first else 2)
+        abi.rt_run(job, launches, probe)
+        if want_mean:
+            out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
+            self.check_flag()
+        return out
+
+    # ------------------------------------------------------------------ Fresnel
     def _reset(self, n_energies):
         for a in self.acc.values():
             a.zero_()
@@ -159,72 +246,6 @@ class ImageFormation:
             abi.fill(self.acc["white"], white_sum)
             self.detect(self.acc["white"], fwhm, scene.psf_sigma, seq + 3, out["white"][ibin])
 
-    def _mean_energy(self, energies, bin_starts):
-        """Experiment.py:485-486, :523 from the running means of the reference accumulator."""
-        r = self.means[:len(energies)].cpu().numpy()
-        per = r.copy()
-        for i in range(1, len(per)):
-            if i not in bin_starts:
-                per[i] = r[i] - r[i - 1]
-        return float(np.dot(per, energies)), float(per.sum())
-
-    # ------------------------------------------------------------------ ray tracing
-    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0):
-        """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526).
-
-        Returns a dict of device tensors [nbins, det_x, det_y] (sample, reference, propag, white)
-        plus ``mean_energy`` = (sum E*mean, sum mean) of Experiment.py:485-486."""
-        s = scene
-        out = self._new_outputs(len(s.thresholds))
-        self._reset(len(s.spectrum))
-        first = point_num == 0
-        if first and want_displacement and self.dx_pad is None:
-            self.dx_pad = torch.zeros((self.nx + 30, self.ny + 30), device=self.device, dtype=torch.float32)
-            self.dy_pad = torch.zeros_like(self.dx_pad)
-        g2 = hm.refraction_gradient_scale(s.d2, s.magnification, s.study_pixel_um)
-        g3 = hm.refraction_gradient_scale(s.d3, s.magnification, s.study_pixel_um)
-        ibin, white_sum, bin_starts = 0, 0.0, {0}
-        for ie, (energy, flux) in enumerate(s.spectrum):
-            k = hm.wavenumber(energy * 1000)
-            i0 = s.mean_shot_count / s.os ** 2 * flux * s.common_factor(energy)      # :438, :451-459
-            plate = s.plate_factor(energy)
-            mem_maps, mem_ub, _ = self._split(s.membrane, energy)
-            smp_maps, smp_ub, _ = self._split(s.sample, energy)
-            if smp_ub != 0.0 or not mem_maps or not smp_maps or len(mem_maps) + len(smp_maps) > abi.MAX_LAYERS:
-                raise NotImplementedError("scene needs 1+ membrane maps, sample maps only, at most %d maps per hop"
-                                          % abi.MAX_LAYERS)
-            # membrane -> object plane (:463-466); uniform layers and the plate only scale the beam
-            self.i_bs.zero_()
-            abi.refract_layers(None, i0 * np.exp(-2 * k * mem_ub) * plate,
-                               [(t, d * g2, 0.0, 2 * k * b) for t, d, b in mem_maps], self.i_bs, flag=self.flag)
-            # object -> detector: sample beam and reference beam in one pass over I_bs (:469-474)
-            layers = [(t, d * g3, d * g3, 0.0) for t, d, b in mem_maps] + \
-                     [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps]
-            abi.refract_layers(self.i_bs, 0.0, layers, self.acc["sample"], self.acc["reference"], flag=self.flag)
-            abi.mean(self.acc["reference"], self.means[ie:ie + 1])
-            if first:
-                # the sample alone (:490-498); the white field is the incident beam itself
-                wd = want_displacement and ie == len(s.spectrum) - 1
-                if wd:
-                    self.dx_pad.zero_()
-                    self.dy_pad.zero_()
-                abi.refract_layers(None, i0 * plate, [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps],
-                                   self.acc["propag"], flag=self.flag,
-                                   dx_pad=self.dx_pad if wd else None, dy_pad=self.dy_pad if wd else None)
-                white_sum += i0 * plate
-            if energy > s.thresholds[ibin] - s.energy_sampling / 2:                  # :501
-                self._close_bin(s, out, ibin, point_num, first, white_sum, sequence_base)
-                ibin += 1
-                if ie + 1 < len(s.spectrum):
-                    for a in self.acc.values():
-                        a.zero_()
-                    white_sum = 0.0
-                    bin_starts.add(ie + 1)
-        out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
-        self.check_flag()
-        return out
-
-    # ------------------------------------------------------------------ Fresnel
     def _fresnel_setup(self):
         if self._plan is None:
             self._plan = abi.FresnelPlan(self.nx, self.ny, 15)
@@ -250,9 +271,9 @@ class ImageFormation:
         """Experiment.computeSampleAndReferenceImages_Fresnel (Experiment.py:279-405)."""
         s = scene
         self._fresnel_setup()
-        out = self._new_outputs(len(s.thresholds))
-        self._reset(len(s.spectrum))
         first = point_num == 0
+        out = self._new_outputs(len(s.thresholds), first)
+        self._reset(len(s.spectrum))
         w_a, w_b = self._waves
         mag_mem_obj = (s.d1 + s.d2) / s.d1                                            # :340
         ibin, white_sum, bin_starts = 0, 0.0, {0}

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _cabi as abi
+from . import transfer
 from .host_api import device
 
 
@@ -26,6 +27,13 @@ class DeviceGeometry:
     def __init__(self, entries, shape):
         self.entries = list(entries)          # torch.Tensor [N, N] float32 | float (uniform thickness)
         self.map_shape = (int(shape[0]), int(shape[1]))
+        self._pending = {}
+        self._host = {}
+
+    def prefetch(self, m=0):
+        """Start copying map ``m`` to pinned host memory; overlaps whatever the GPU does next."""
+        if m not in self._host and m not in self._pending and isinstance(self.entries[m], torch.Tensor):
+            self._pending[m] = transfer.Pending(self.entries[m])
 
     @property
     def shape(self):
@@ -36,9 +44,12 @@ class DeviceGeometry:
 
     def __getitem__(self, m):
         e = self.entries[m]
-        if isinstance(e, torch.Tensor):
-            return e.cpu().numpy()
-        return np.full(self.map_shape, e, dtype=np.float32)
+        if not isinstance(e, torch.Tensor):
+            return np.full(self.map_shape, e, dtype=np.float32)
+        if m not in self._host:
+            self.prefetch(m)
+            self._host[m] = self._pending.pop(m).wait()
+        return self._host[m]
 
     def __array__(self, dtype=None, copy=None):
         stack = np.stack([np.asarray(self[m], dtype=np.float64) for m in range(len(self.entries))])
@@ -64,7 +75,7 @@ def from_host(array):
         if lo == hi:
             entries.append(lo)
         else:
-            entries.append(torch.as_tensor(np.ascontiguousarray(arr[m], dtype=np.float32)).to(device()))
+            entries.append(transfer.upload(arr[m], torch.float32, device()))
     return DeviceGeometry(entries, arr.shape[1:])
 
 
@@ -103,13 +114,13 @@ def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
         shifted[:, 0] += ext_y
         tab = np.concatenate((tab, shifted), axis=0)
         ext_y += step
-    dev_tab = torch.as_tensor(np.ascontiguousarray(tab)).to(device())
+    dev_tab = transfer.upload(tab, torch.float64, device())
     _sphere_cache.clear()
     _sphere_cache[key] = (dev_tab, ext_x, ext_y)
     return _sphere_cache[key]
 
 
-def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None):
+def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):
     """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171).
 
     Two ``np.random.randint`` draws per layer, x first, from numpy's global stream (:139-140),
@@ -128,7 +139,10 @@ def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=Non
     params = {'Average sphere radius': (sample.myMeanSphereRadius, 'um'),
               'Number of layers': (sample.myNbOfLayers, ''),
               'Support total thickness': (support_um, 'um')}
-    return DeviceGeometry([grains, support_um * 1e-6], (dim_x, dim_y)), params
+    geom = DeviceGeometry([grains, support_um * 1e-6], (dim_x, dim_y))
+    if prefetch:
+        geom.prefetch(0)      # main.py:99 saves this map: start the copy now, it overlaps the image formation
+    return geom, params
 
 
 # ---------------------------------------------------------------------------- samples

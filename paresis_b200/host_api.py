@@ -22,14 +22,14 @@ def device():
 
 
 def to_dev(a, dtype=torch.float32):
-    a = np.ascontiguousarray(a)
-    if not a.flags.writeable:
-        a = a.copy()
-    return torch.as_tensor(a).to(device(), dtype=dtype).contiguous()
+    from . import transfer
+    return transfer.upload(a, dtype, device())
 
 
 def to_host(t, dtype=np.float64):
-    return t.cpu().numpy().astype(dtype)
+    from . import transfer
+    torch_dtype = {np.float64: torch.float64, np.float32: torch.float32, np.complex128: torch.complex128}.get(dtype)
+    return transfer.fetch(t, torch_dtype) if torch_dtype is not None else t.cpu().numpy().astype(dtype)
 
 
 class InsaneValues(Exception):
@@ -88,15 +88,11 @@ def detection(image, source_fwhm_px, oversampling, det_dims, psf_sigma, poisson=
         psf = to_dev(hm.gaussian_1d(psf_sigma))
     work = torch.empty(abi.detect_work_floats(image.shape[0], image.shape[1], int(oversampling), dx, dy),
                        device=dev, dtype=torch.float32)
-    expect = torch.empty((dx, dy), device=dev, dtype=torch.float32)
-    abi.detect(to_dev(image), int(oversampling), dx, dy, src, psf, work, expect)
-    if not poisson:
-        return to_host(expect)
+    out = torch.empty((dx, dy), device=dev, dtype=torch.float32)
     if seed is None:
         seed = int(np.floor(time.time() * 100 % (2 ** 32 - 1)))   # Detector.py:113
-    counts = torch.empty_like(expect)
-    abi.poisson(expect, counts, seed, sequence)
-    return to_host(counts)
+    abi.detect_counts(to_dev(image), int(oversampling), dx, dy, src, psf, work, out, poisson, seed, sequence)
+    return to_host(out)
 
 
 _plans = {}

@@ -224,6 +224,16 @@ def test_detection(abi, golden):
         out = torch.empty((d0, d1), device="cuda")
         abi.detect(img, os_, d0, d1, src, pk, work, out)
         assert rel_l2(out.cpu().numpy(), g["det%d_out" % kcase]) < 1e-6, kcase
+        # the fused single-kernel path (production) gives the same expectation ...
+        fused = torch.empty((d0, d1), device="cuda")
+        abi.detect_counts(img, os_, d0, d1, src, pk, work, fused, False)
+        assert rel_l2(fused.cpu().numpy(), g["det%d_out" % kcase]) < 1e-6, kcase
+        # ... and Poisson counts around it
+        counts = torch.empty((d0, d1), device="cuda")
+        abi.detect_counts(img, os_, d0, d1, src, pk, work, counts, True, 99, kcase)
+        ok = fused > 10.0          # (one synthetic input dips below zero: lambda <= 0 draws 0)
+        z = ((counts - fused) / fused.clamp_min(1.0).sqrt())[ok].double()
+        assert torch.equal(counts, counts.round()) and abs(z.mean().item()) < 0.08 and abs(z.std().item() - 1) < 0.08, kcase
     out = torch.empty((30, 45), device="cuda")
     abi.bin_sum(dev(g["resize_in"]), 30, 45, out)
     assert rel_l2(out.cpu().numpy(), g["resize_2"]) < 1e-6

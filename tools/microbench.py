@@ -116,19 +116,34 @@ def main():
         t_smp = torch.empty((n, n), device=dev)
         abi.sphere_map(1000.0 * n / 400, n, n, 2.9256, t_smp)
         ibs = torch.zeros((n, n), device=dev)
-        med, best = timeit(lambda: abi.refract_layers(None, 7500.0, [(t_mem, 5.97e-7 * s2, 0.0, 2 * k * 5.37e-9)], ibs), flush=flush)
-        rec("refract_membrane_hop", n, med, best, 8 * px)
         o1 = torch.zeros((n, n), device=dev); o2 = torch.zeros((n, n), device=dev)
         layers = [(t_mem, 5.97e-7 * s3, 5.97e-7 * s3, 0.0), (t_smp, 9.85e-8 * s3, 0.0, 2 * k * 3.16e-12)]
-        med, best = timeit(lambda: abi.refract_layers(ibs, 0.0, layers, o1, o2), flush=flush)
-        rec("refract_sample_ref_hop", n, med, best, 20 * px)
+        for mode in (0, 2):
+            abi.set_tuning(0, mode)
+            for rows in (0, 8, 16, 32):
+                abi.set_tuning(1, rows)
+                med, best = timeit(lambda: abi.refract_layers(None, 7500.0, [(t_mem, 5.97e-7 * s2, 0.0, 2 * k * 5.37e-9)], ibs), flush=flush)
+                rec("refract_membrane_hop", n, med, best, 8 * px, mode=mode, rows=rows)
+                med, best = timeit(lambda: abi.refract_layers(ibs, 0.0, layers, o1, o2), flush=flush)
+                rec("refract_sample_ref_hop", n, med, best, 20 * px, mode=mode, rows=rows)
+        abi.set_tuning(0, 2); abi.set_tuning(1, 0)
+        # the same hop with its outputs warm in L2 (zero-filled just before, as the pipeline does)
+        def hop_warm():
+            o1.zero_(); o2.zero_()
+            abi.refract_layers(ibs, 0.0, layers, o1, o2)
+        med, best = timeit(hop_warm, flush=flush)
+        rec("memset2+refract_sample_ref_hop", n, med, best, 20 * px)
         det = n // 2
         work = torch.empty(abi.detect_work_floats(n, n, 2, det, det), device=dev)
         expect = torch.empty((det, det), device=dev)
         src = torch.as_tensor(hm.gaussian_1d(0.424 / 2.355), device=dev, dtype=torch.float32)
         psf = torch.as_tensor(hm.gaussian_1d(1.2), device=dev, dtype=torch.float32)
         med, best = timeit(lambda: abi.detect(o1, 2, det, det, src, psf, work, expect), flush=flush)
-        rec("detect", n, med, best, 4 * px + 4 * det * det)
+        rec("detect_4pass", n, med, best, 4 * px + 4 * det * det)
+        med, best = timeit(lambda: abi.detect_counts(o1, 2, det, det, src, psf, work, expect, False), flush=flush)
+        rec("detect_fused_nonoise", n, med, best, 4 * px + 4 * det * det)
+        med, best = timeit(lambda: abi.detect_counts(o1, 2, det, det, src, psf, work, expect, True, 1, 2), flush=flush)
+        rec("detect_fused_poisson", n, med, best, 4 * px + 4 * det * det)
         counts = torch.empty((det, det), device=dev)
         med, best = timeit(lambda: abi.poisson(expect, counts, 1, 2), flush=flush)
         rec("poisson", n, med, best, 8 * det * det)
