@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -81,11 +81,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line)
 
+    def mark(self):
+        """Samples taken from here on count (the sampler itself starts earlier: nvidia-smi needs ~0.3 s to spin up)."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        self.lines = self.lines[getattr(self, "first", 0):] or self.lines[-3:]
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.lines:
@@ -168,6 +173,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 32))
     per_step = workers                      # bounded sample: one position per worker per step
+    # a step of the CPU arm takes ~10-15 s: cap the run to a few minutes whatever K / W were asked for
+    args.steps, args.warmup = min(args.steps, 5), min(args.warmup, 1)
     with mp.get_context("fork").Pool(workers, initializer=_worker_init) as pool:
         for w in range(args.warmup):
             pool.map(_worker_run, [(1, 5000 + w * per_step + i) for i in range(per_step)])
@@ -248,7 +255,7 @@ def run_gpu(args):
     def api_job(step):
         """The same job through the reference-facing API: host results, membrane map copied back."""
         np.random.seed((20_000 * rank + step + 7) % (2 ** 32))
-        geometry._sphere_cache.clear()                      # the sphere list crosses PCIe once per job
+        geometry.drop_device_tables()                       # the sphere list crosses PCIe once per job
         h0, d0 = transfer.bytes_h2d, transfer.bytes_d2h
         exp.myDetector.det_param["myBinsThersholds"] = []    # position 0 closes the last bin in place (Experiment.py:429)
         with contextlib.redirect_stdout(io.StringIO()):
@@ -274,13 +281,14 @@ def run_gpu(args):
     k_events = []
 
     # ---- timed region: device-resident job
+    sampler = ClockSampler(local)
+    sampler.start()
     for w in range(args.warmup):
         device_job(1000 + w)
     abi.profile_only = dominant if dominant not in abi.PROBE else None
     abi.profile_events = []
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     launches0 = abi.launches
     step_events = []
     wall0 = time.perf_counter()
@@ -336,7 +344,8 @@ def run_gpu(args):
                                   timing="CUDA events per step on the launching stream, max over ranks",
                                   wall_ms_per_step=wall / args.steps * 1e3),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                    "pinned_buffers_allocated": transfer.pinned_allocs},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -374,8 +383,8 @@ def profile_kernels(abi, job, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -217,10 +217,14 @@ int paresis_bin_sum(const float* image, int nx, int ny, int size_x, int size_y, 
  * spherical caps, all layers.  spheres[n][3] = (c0, c1, radius) in micrometres, already
  * rescaled / shifted / tiled (:95-124, done on the host).  offsets_host[layer][2] = the two
  * np.random.randint draws per layer (:139-140), x first.  thickness_out[dim_x][dim_y] is
- * overwritten, in metres. */
+ * overwritten, in metres.  `work` is device scratch for the list of bounding-box chunks
+ * (paresis_raster_work_bytes suggests a size; a list that overflows is still rasterised
+ * correctly, only slower). */
+size_t paresis_raster_work_bytes(int n_spheres, int n_layers, int dim_x, int dim_y);
 int paresis_raster_spheres(const double* spheres, int n_spheres, double pix_um,
                            const int64_t* offsets_host, int n_layers, int dim_x, int dim_y,
-                           int margin, float* thickness_out, paresis_stream stream);
+                           int margin, float* thickness_out, void* work, size_t work_bytes,
+                           paresis_stream stream);
 
 /* CreateSampleSphere -- Samples/createSampGeom.py:41-53. */
 int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, float* out,

@@ -253,8 +253,18 @@ class Experiment:
         host = transfer.fetch(res["_stack"], torch.float64)       # one cast + one PCIe copy for all images
         out = [host[i] for i in range(host.shape[0])]
         while len(out) < 4:
-            out.append(np.zeros(out[0].shape))
+            out.append(self._zeros(out[0].shape))
         return out
+
+    def _zeros(self, shape):
+        """All-zero result images are shared, read-only arrays (allocating 8-32 MB of zeros per call costs
+        more than the GPU work of a position)."""
+        cache = self.__dict__.setdefault("_zero_cache", {})
+        if shape not in cache:
+            z = np.zeros(shape)
+            z.setflags(write=False)
+            cache[shape] = z
+        return cache[shape]
 
     def computeSampleAndReferenceImages_Fresnel(self, pointNum):
         """All images of one membrane position with the Fresnel propagator (Experiment.py:279-405).
@@ -295,7 +305,7 @@ class Experiment:
             self.Dxreal = transfer.fetch(eng.dx_pad, torch.float64)
             self.Dyreal = transfer.fetch(eng.dy_pad, torch.float64)
         n = self.exp_dict['studyDimensions']
-        self.darkFieldPropag = np.zeros((n[0], n[1]))
+        self.darkFieldPropag = self._zeros((int(n[0]), int(n[1])))
         print("Mean detected energy in reference image", self.exp_dict['meanEnergy'])
         return out[0], out[1], out[2], out[3], self.Dxreal, self.Dyreal, self.darkFieldPropag
 

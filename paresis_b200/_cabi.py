@@ -24,7 +24,7 @@ EXPORTS = (
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
     "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_detect_work_floats", "paresis_detect",
     "paresis_detect_counts",
-    "paresis_poisson", "paresis_bin_sum", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
+    "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run",
 )
 
@@ -91,7 +91,7 @@ def _load():
         "paresis_detect_counts": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, ci, u64, u64, vp],
         "paresis_poisson": [vp, vp, sz, u64, u64, vp],
         "paresis_bin_sum": [vp, ci, ci, ci, ci, vp, vp],
-        "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp],
+        "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp, sz, vp],
         "paresis_sphere_map": [cd, ci, ci, cd, vp, vp],
         "paresis_cylinder_map": [cd, cd, ci, ci, cd, vp, vp],
         "paresis_fill": [vp, cf, sz, vp],
@@ -108,6 +108,8 @@ def _load():
     lib.paresis_detect_work_floats.restype = sz
     lib.paresis_fresnel_plan_bytes.argtypes = [vp]
     lib.paresis_fresnel_plan_bytes.restype = sz
+    lib.paresis_raster_work_bytes.argtypes = [ci, ci, ci, ci]
+    lib.paresis_raster_work_bytes.restype = sz
     return lib
 
 
@@ -332,12 +334,21 @@ def bin_sum(image, size_x, size_y, out):
     _count()
 
 
+_raster_work = {}
+
+
 def raster_spheres(spheres, pix_um, offsets, dim_x, dim_y, margin, out):
     offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(-1, 2))
+    need = lib.paresis_raster_work_bytes(spheres.shape[0], offs.shape[0], dim_x, dim_y)
+    key = out.device.index
+    work = _raster_work.get(key)
+    if work is None or work.numel() < need:
+        work = _raster_work[key] = torch.empty(need, device=out.device, dtype=torch.uint8)
     _check(_timed("raster_spheres", lambda: lib.paresis_raster_spheres(
         _ptr(spheres, torch.float64), spheres.shape[0], float(pix_um), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-        offs.shape[0], dim_x, dim_y, margin, _ptr(out, torch.float32), _stream())), "paresis_raster_spheres")
-    _count()
+        offs.shape[0], dim_x, dim_y, margin, _ptr(out, torch.float32), ctypes.c_void_p(work.data_ptr()), work.numel(),
+        _stream())), "paresis_raster_spheres")
+    _count(2)
 
 
 def sphere_map(radius_um, dim_x, dim_y, pix_um, out):

@@ -189,8 +189,7 @@ __device__ __forceinline__ float log_poisson_pmf(float k, float lam) {
 //              variables", Insur. Math. Econ. 12 (1993).  ~86 % of the draws end at the quick
 //              acceptance test; the full test uses the cancellation-free fp32 log-pmf above, so a
 //              warp never waits on fp64 transcendentals.
-__device__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
-    if (!(lam > 0.f)) return 0.f;
+__device__ __forceinline__ Philox poisson_stream(uint64_t seed, uint64_t seq, uint64_t pixel) {
     Philox g;
     g.c[0] = (uint32_t)pixel;
     g.c[1] = 0u;
@@ -198,9 +197,31 @@ __device__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t p
     g.c[3] = (uint32_t)(seq >> 32) ^ (uint32_t)(pixel >> 32);
     g.k[0] = (uint32_t)seed;
     g.k[1] = (uint32_t)(seed >> 32);
+    return g;
+}
+
+struct PtrsSetup {
+    float b, a, vr;
+    __device__ __forceinline__ explicit PtrsSetup(float lam) {
+        const float slam = sqrtf(lam);
+        b = 0.931f + 2.53f * slam;
+        a = -0.059f + 0.02483f * b;
+        vr = 0.9277f - 3.6224f / (b - 2.0f);
+    }
+    // k = floor((2a/us + b) U + lam + 0.43): the sum is formed in fp64 so large means keep unit resolution
+    __device__ __forceinline__ float candidate(float lam, float U, float us) const {
+        return (float)floor((double)((2.0f * a / us + b) * U) + (double)lam + 0.43);
+    }
+};
+
+// The cheap part of a draw: everything except PTRS trials that fail the quick acceptance test.
+// Returns true and the variate when it is decided here (lam <= 0, lam < 10, or trial 0 accepted).
+__device__ __forceinline__ bool poisson_quick(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, float& result) {
+    if (!(lam > 0.f)) { result = 0.f; return true; }
+    Philox g = poisson_stream(seed, seq, pixel);
     uint32_t r[4];
+    g.generate(r);
     if (lam < 10.f) {
-        g.generate(r);
         const float u = (float)u01d(r[0], r[1]);
         float p = expf(-lam), F = p;
         int x = 0;
@@ -209,25 +230,39 @@ __device__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t p
             p *= lam / (float)x;
             F += p;
         }
-        return (float)x;
+        result = (float)x;
+        return true;
     }
-    const float slam = sqrtf(lam);
-    const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
-    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
-    const float log_invalpha = logf(1.1239f + 1.1328f / (b - 3.4f));
+    const PtrsSetup t(lam);
+    const float U = u01f(r[0]) - 0.5f, V = u01f(r[1]);
+    const float us = 0.5f - fabsf(U);
+    result = t.candidate(lam, U, us);
+    return us >= 0.07f && V <= t.vr;
+}
+
+// The full PTRS loop for lam >= 10 (same stream as poisson_quick: trial 0 is replayed first).
+__device__ float poisson_ptrs(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
+    Philox g = poisson_stream(seed, seq, pixel);
+    uint32_t r[4];
+    const PtrsSetup t(lam);
+    const float log_invalpha = logf(1.1239f + 1.1328f / (t.b - 3.4f));
     for (uint32_t trial = 0; trial < 64; ++trial) {
         g.c[1] = trial;
         g.generate(r);
         const float U = u01f(r[0]) - 0.5f, V = u01f(r[1]);
         const float us = 0.5f - fabsf(U);
-        // k = floor((2a/us + b) U + lam + 0.43): the sum is formed in fp64 so large means keep unit resolution
-        const float k = (float)floor((double)((2.0f * a / us + b) * U) + (double)lam + 0.43);
-        if (us >= 0.07f && V <= vr) return k;
+        const float k = t.candidate(lam, U, us);
+        if (us >= 0.07f && V <= t.vr) return k;
         if (k < 0.f || (us < 0.013f && V > us)) continue;
-        if (logf(V) + log_invalpha - logf(a / (us * us) + b) <= log_poisson_pmf(k, lam))
-            return k;
+        if (logf(V) + log_invalpha - logf(t.a / (us * us) + t.b) <= log_poisson_pmf(k, lam)) return k;
     }
     return floorf(lam + 0.5f);  // unreachable in practice (acceptance > 0.9 per trial)
+}
+
+__device__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
+    float x;
+    if (poisson_quick(lam, seed, seq, pixel, x)) return x;
+    return poisson_ptrs(lam, seed, seq, pixel);
 }
 
 __global__ void __launch_bounds__(256)
@@ -268,6 +303,9 @@ detect_fused_kernel(const float* __restrict__ img, FusedShape s, const float* __
     float* W = B + s.bw * s.bw;                   // composite kernel, os + 2*src_half taps
     float* P = W + (s.os + 2 * s.src_half);       // PSF kernel, 2*psf_half + 1 taps
     int* rowoff = (int*)(P + 2 * s.psf_half + 1); // [sw] source row offset (elements) or -1 = zero row
+    int* queue = rowoff + s.sw;                   // [TB*TB][2] pixels whose Poisson draw needs the full PTRS test
+    __shared__ int n_queued;
+    if (threadIdx.x == 0 && threadIdx.y == 0) n_queued = 0;
     const int tid = threadIdx.y * FUSED_TX + threadIdx.x;
     const int taps = TAPS > 0 ? TAPS : s.os + 2 * s.src_half;
     const int pad = DET_PAD * s.os, npx = s.nx + 2 * pad, npy = s.ny + 2 * pad;
@@ -365,7 +403,26 @@ detect_fused_kernel(const float* __restrict__ img, FusedShape s, const float* __
         float acc = 0.f;
         for (int k = 0; k < np; ++k) acc = fmaf(P[k], src[k * TB], acc);
         const size_t p = (size_t)da * s.det_y + db;
-        out[p] = NOISE ? poisson_draw(acc, seed, seq, p) : acc;
+        if (!NOISE) { out[p] = acc; continue; }
+        // ~86 % of the draws finish at the quick acceptance test; the rest are queued so that the
+        // expensive tail runs on dense warps instead of dragging every warp through it
+        float x;
+        if (poisson_quick(acc, seed, seq, p, x)) {
+            out[p] = x;
+        } else {
+            const int slot = atomicAdd(&n_queued, 1);
+            queue[2 * slot] = a * TB + threadIdx.x;
+            queue[2 * slot + 1] = __float_as_int(acc);
+        }
+    }
+    if (NOISE) {
+        __syncthreads();
+        for (int qi = tid; qi < n_queued; qi += FUSED_THREADS) {
+            const int local = queue[2 * qi];
+            const float lam = __int_as_float(queue[2 * qi + 1]);
+            const size_t p = (size_t)(blockIdx.y * TB + local / TB) * s.det_y + (blockIdx.x * TB + local % TB);
+            out[p] = poisson_ptrs(lam, seed, seq, p);
+        }
     }
 }
 
@@ -452,7 +509,8 @@ extern "C" int paresis_detect(const float* image, int nx, int ny, int os, int de
 }
 
 static size_t fused_smem_bytes(const FusedShape& s) {
-    const size_t floats = (size_t)s.sw * s.bw + (size_t)s.bw * s.bw + (s.os + 2 * s.src_half) + (2 * s.psf_half + 1) + s.sw;
+    const size_t floats = (size_t)s.sw * s.bw + (size_t)s.bw * s.bw + (s.os + 2 * s.src_half) + (2 * s.psf_half + 1) + s.sw
+                          + 2 * TB * TB;
     return floats * sizeof(float);
 }
 

@@ -79,8 +79,15 @@ __global__ void __launch_bounds__(EW_THREADS) axpy_kernel(float* dst, const floa
 }
 
 __global__ void __launch_bounds__(EW_THREADS) sum_kernel(const float* __restrict__ src, size_t n, double scale, double* out) {
+    // float4 loads (cudaMalloc'd images are 16-byte aligned), fp32 partial sums of 4, fp64 across iterations
     double acc = 0.0;
-    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
+    const size_t n4 = (((uintptr_t)src & 15) == 0) ? n / 4 : 0;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n4; p += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src4 + p);
+        acc += (double)((v.x + v.y) + (v.z + v.w));
+    }
+    for (size_t p = 4 * n4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
         acc += (double)src[p];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     __shared__ double part[EW_THREADS / 32];

@@ -16,62 +16,80 @@ struct LayerOffsets {
     long long y[MAX_MEMBRANE_LAYERS];
 };
 
-// One thread per (layer, sphere) candidate: cull against the reference's acceptance window (:151)
-// and against the field of view, compact the few survivors (~3 %) of the block into shared
-// memory, then the block sweeps each survivor's bounding box (:155-159) and adds
-// 2*sqrt(r^2 - d^2) with REDG.ADD.F32.  The cancelling difference r^2 - d^2 stays in fp64.
+// Two kernels.  cull: one thread per (layer, sphere) candidate tests the reference's acceptance
+// window (:151) and the field of view; a survivor (~3 %) cuts its bounding box (:155-159) into
+// chunks of RASTER_CHUNK cells and appends one work item per chunk to a list in `work`.
+// fill: warps walk that list, so the cost of a rare 100-pixel grain is spread over many warps
+// instead of stalling one block.  Each cell adds 2*sqrt(r^2 - d^2) with REDG.ADD.F32; the
+// cancelling difference r^2 - d^2 stays in fp64.
 constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_CHUNK = 512;
 
-struct SphereHit {
+struct RasterItem {
     double xf, yf, rad;
-    int x, y;
+    int x, y, chunk, pad_;
 };
 
+__device__ __forceinline__ void raster_chunk(const RasterItem& h, int lane, int nlanes, double scale_m, int dim_x, int dim_y,
+                                             int margin, float* __restrict__ out) {
+    const int reach = (int)floor(h.rad) + 1;
+    const int w = 2 * reach;
+    const double r2 = h.rad * h.rad;
+    const double ex0 = (double)h.x - h.xf, ey0 = (double)h.y - h.yf;
+    const unsigned magic = 0xffffffffu / (unsigned)w + 1u;   // idx / w == umulhi(idx, magic) for idx < w*w <= 2^20
+    const int r0 = h.x - reach - margin, c0 = h.y - reach - margin;   // canvas -> cropped field of view (:161)
+    const int end = min((h.chunk + 1) * RASTER_CHUNK, w * w);
+    const float two_scale = 2.0f * (float)scale_m;
+    for (int idx = h.chunk * RASTER_CHUNK + lane; idx < end; idx += nlanes) {
+        const int q = (int)__umulhi((unsigned)idx, magic);
+        const int p = idx - q * w;
+        const int r = r0 + q, c = c0 + p;
+        if ((unsigned)r >= (unsigned)dim_x || (unsigned)c >= (unsigned)dim_y) continue;
+        const double ex = (double)(q - reach) + ex0, ey = (double)(p - reach) + ey0;
+        const float diff = (float)(r2 - (ex * ex + ey * ey));
+        if (diff > 0.f) {
+            float inv;   // sqrt(x) = x * rsqrt(x): one MUFU, ~2 ulp, no IEEE fix-up code in the inner loop
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(diff));
+            red_add(out + (size_t)r * dim_y + c, two_scale * (diff * inv));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS)
-raster_spheres_kernel(const double* __restrict__ spheres, int n, double pix, double scale_m, LayerOffsets off,
-                      int n_layers, int dim_x, int dim_y, int margin, float* __restrict__ out) {
-    __shared__ SphereHit hits[RASTER_THREADS];
-    __shared__ int n_hits;
-    if (threadIdx.x == 0) n_hits = 0;
-    __syncthreads();
+raster_cull_kernel(const double* __restrict__ spheres, int n, double pix, double scale_m, LayerOffsets off, int n_layers,
+                   int dim_x, int dim_y, int margin, float* __restrict__ out, int* __restrict__ count,
+                   RasterItem* __restrict__ items, int capacity) {
     const long long id = (long long)blockIdx.x * RASTER_THREADS + threadIdx.x;
-    if (id < (long long)n * n_layers) {
-        const int layer = (int)(id / n), s = (int)(id % n);
-        const int margin2 = margin / 2;
-        SphereHit h;
-        h.rad = spheres[3 * s + 2] / pix;
-        h.xf = spheres[3 * s + 1] / pix - (double)off.x[layer];
-        h.yf = spheres[3 * s + 0] / pix - (double)off.y[layer];
-        const long long x = __double2ll_rn(h.xf), y = __double2ll_rn(h.yf);   // np.round: half to even (:149-150)
-        const long long reach = (long long)floor(h.rad) + 1;
-        const bool accepted = margin2 < x && x < dim_x + margin + margin2 && margin2 < y && y < dim_y + margin + margin2;
-        const bool visible = x + reach > margin && x - reach < dim_x + margin && y + reach > margin && y - reach < dim_y + margin;
-        if (accepted && visible) {
-            h.x = (int)x; h.y = (int)y;
-            hits[atomicAdd(&n_hits, 1)] = h;
-        }
+    if (id >= (long long)n * n_layers) return;
+    const int layer = (int)(id / n), s = (int)(id % n);
+    const int margin2 = margin / 2;
+    RasterItem h;
+    h.rad = spheres[3 * s + 2] / pix;
+    h.xf = spheres[3 * s + 1] / pix - (double)off.x[layer];
+    h.yf = spheres[3 * s + 0] / pix - (double)off.y[layer];
+    const long long x = __double2ll_rn(h.xf), y = __double2ll_rn(h.yf);   // np.round: half to even (:149-150)
+    const long long reach = (long long)floor(h.rad) + 1;
+    const bool accepted = margin2 < x && x < dim_x + margin + margin2 && margin2 < y && y < dim_y + margin + margin2;
+    const bool visible = x + reach > margin && x - reach < dim_x + margin && y + reach > margin && y - reach < dim_y + margin;
+    if (!(accepted && visible) || reach > 500) return;   // (a 500-pixel grain would already exceed the canvas margin)
+    h.x = (int)x; h.y = (int)y; h.pad_ = 0;
+    const int cells = (int)(4 * reach * reach);
+    const int chunks = (cells + RASTER_CHUNK - 1) / RASTER_CHUNK;
+    const int base = atomicAdd(count, chunks);
+    for (int k = 0; k < chunks; ++k) {
+        h.chunk = k;
+        if (base + k < capacity) items[base + k] = h;
+        else raster_chunk(h, 0, 1, scale_m, dim_x, dim_y, margin, out);   // list full: do it here, slowly but correctly
     }
-    __syncthreads();
-    // the whole block sweeps one survivor at a time: a rare 100-pixel grain costs 8x less tail than
-    // it would on a single warp
-    for (int e = 0; e < n_hits; ++e) {
-        const SphereHit h = hits[e];
-        const int reach = (int)floor(h.rad) + 1;
-        const int w = 2 * reach;
-        const double r2 = h.rad * h.rad;
-        const double ex0 = (double)h.x - h.xf, ey0 = (double)h.y - h.yf;
-        const unsigned magic = 0xffffffffu / (unsigned)w + 1u;   // idx / w == umulhi(idx, magic) for idx < w*w <= 2^20
-        const int r0 = h.x - reach - margin, c0 = h.y - reach - margin;   // canvas -> cropped field of view (:161)
-        for (int idx = threadIdx.x; idx < w * w; idx += RASTER_THREADS) {
-            const int q = (int)__umulhi((unsigned)idx, magic);
-            const int p = idx - q * w;
-            const int r = r0 + q, c = c0 + p;
-            if ((unsigned)r >= (unsigned)dim_x || (unsigned)c >= (unsigned)dim_y) continue;
-            const double ex = (double)(q - reach) + ex0, ey = (double)(p - reach) + ey0;
-            const double diff = r2 - (ex * ex + ey * ey);
-            if (diff > 0.0) red_add(out + (size_t)r * dim_y + c, 2.0f * sqrtf((float)diff) * (float)scale_m);
-        }
-    }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_fill_kernel(const int* __restrict__ count, const RasterItem* __restrict__ items, int capacity, double scale_m,
+                   int dim_x, int dim_y, int margin, float* __restrict__ out) {
+    const int n_items = min(*count, capacity);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * RASTER_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * RASTER_THREADS) >> 5;
+    for (int e = warp; e < n_items; e += n_warps) raster_chunk(items[e], lane, 32, scale_m, dim_x, dim_y, margin, out);
 }
 
 __global__ void sphere_map_kernel(double rad, double scale_m, int dim_x, int dim_y, float* __restrict__ out) {
@@ -121,12 +139,19 @@ __global__ void cylinder_map_kernel(Affine inv, double rad, double scale_m, int 
 
 using namespace paresis;
 
+extern "C" size_t paresis_raster_work_bytes(int n_spheres, int n_layers, int dim_x, int dim_y) {
+    (void)n_spheres;
+    const size_t items = (size_t)dim_x * dim_y * (size_t)(n_layers > 0 ? n_layers : 1) / 128 + 65536;
+    return 16 + items * sizeof(RasterItem);
+}
+
 extern "C" int paresis_raster_spheres(const double* spheres, int n_spheres, double pix_um,
                                       const int64_t* offsets_host, int n_layers, int dim_x, int dim_y,
-                                      int margin, float* thickness_out, paresis_stream stream) {
+                                      int margin, float* thickness_out, void* work, size_t work_bytes,
+                                      paresis_stream stream) {
     if (!spheres || !offsets_host || !thickness_out || n_spheres < 0 || n_layers < 1 || n_layers > MAX_MEMBRANE_LAYERS ||
-        dim_x < 1 || dim_y < 1 || margin < 0 || !(pix_um > 0)) {
-        set_last_error("paresis_raster_spheres: bad arguments (layers 1..%d)", MAX_MEMBRANE_LAYERS);
+        dim_x < 1 || dim_y < 1 || margin < 0 || !(pix_um > 0) || !work || work_bytes < 16 + sizeof(RasterItem)) {
+        set_last_error("paresis_raster_spheres: bad arguments (layers 1..%d, work buffer required)", MAX_MEMBRANE_LAYERS);
         return PARESIS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -137,11 +162,18 @@ extern "C" int paresis_raster_spheres(const double* spheres, int n_spheres, doub
         off.x[l] = offsets_host[2 * l];
         off.y[l] = offsets_host[2 * l + 1];
     }
+    int* count = (int*)work;
+    RasterItem* items = (RasterItem*)((char*)work + 16);
+    const int capacity = (int)((work_bytes - 16) / sizeof(RasterItem));
+    PARESIS_CUDA(cudaMemsetAsync(count, 0, sizeof(int), s));
     const long long candidates = (long long)n_spheres * n_layers;
     const int blocks = (int)((candidates + RASTER_THREADS - 1) / RASTER_THREADS);
-    raster_spheres_kernel<<<blocks, RASTER_THREADS, 0, s>>>(spheres, n_spheres, pix_um, pix_um * 1e-6, off,
-                                                             n_layers, dim_x, dim_y, margin, thickness_out);
-    PARESIS_LAUNCH_CHECK("raster_spheres_kernel");
+    raster_cull_kernel<<<blocks, RASTER_THREADS, 0, s>>>(spheres, n_spheres, pix_um, pix_um * 1e-6, off, n_layers, dim_x,
+                                                          dim_y, margin, thickness_out, count, items, capacity);
+    PARESIS_LAUNCH_CHECK("raster_cull_kernel");
+    raster_fill_kernel<<<148 * 4, RASTER_THREADS, 0, s>>>(count, items, capacity, pix_um * 1e-6, dim_x, dim_y, margin,
+                                                           thickness_out);
+    PARESIS_LAUNCH_CHECK("raster_fill_kernel");
     return PARESIS_OK;
 }
 

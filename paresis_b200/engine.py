@@ -155,29 +155,28 @@ class ImageFormation:
         return float(np.dot(per, energies)), float(per.sum())
 
     # ------------------------------------------------------------------ ray tracing
-    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True):
-        """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526) as one library
-        call (paresis_rt_run).
+    def bins(self, scene):
+        """Spectrum indices of each detector bin (closing rule of Experiment.py:501)."""
+        out, cur, ibin = [], [], 0
+        for ie, (energy, _) in enumerate(scene.spectrum):
+            cur.append(ie)
+            if energy > scene.thresholds[ibin] - scene.energy_sampling / 2:
+                out.append(cur)
+                cur, ibin = [], ibin + 1
+        if cur:
+            out.append(cur)     # energies after the last threshold never reach the detector (as upstream)
+        return out
 
-        Returns a dict of device tensors [nbins, det_x, det_y]: sample, reference (+ propag, white
-        at position 0; absent keys are all-zero images), plus ``mean_energy`` = (sum E*mean,
-        sum mean) of Experiment.py:485-486."""
+    def _rt_energies(self, scene, indices, closing):
+        """ctypes array of per-energy hop scalars for the spectrum entries ``indices``; ``closing`` =
+        set of spectrum indices after which the detector runs."""
         s = scene
-        first = point_num == 0
-        nbins = len(s.thresholds)
-        n_e = len(s.spectrum)
-        out = self._new_outputs(nbins, first)
-        if n_e > self.means.numel():
-            self.means = torch.zeros(n_e, device=self.device, dtype=torch.float64)
-        wd = first and want_displacement
-        if wd and self.dx_pad is None:
-            self.dx_pad = torch.empty((self.nx + 30, self.ny + 30), device=self.device, dtype=torch.float32)
-            self.dy_pad = torch.empty_like(self.dx_pad)
         g2 = hm.refraction_gradient_scale(s.d2, s.magnification, s.study_pixel_um)
         g3 = hm.refraction_gradient_scale(s.d3, s.magnification, s.study_pixel_um)
-        energies = (abi.RtEnergy * n_e)()
-        ibin, bin_starts, keep = 0, {0}, []
-        for ie, (energy, flux) in enumerate(s.spectrum):
+        energies = (abi.RtEnergy * len(indices))()
+        keep = []
+        for slot, ie in enumerate(indices):
+            energy, flux = s.spectrum[ie]
             k = hm.wavenumber(energy * 1000)
             i0 = s.mean_shot_count / s.os ** 2 * flux * s.common_factor(energy)      # :438, :451-459
             plate = s.plate_factor(energy)
@@ -186,7 +185,7 @@ class ImageFormation:
             if smp_ub != 0.0 or not mem_maps or not smp_maps or len(mem_maps) + len(smp_maps) > abi.MAX_LAYERS:
                 raise NotImplementedError("scene needs 1+ membrane maps, sample maps only, at most %d maps per hop"
                                           % abi.MAX_LAYERS)
-            en = energies[ie]
+            en = energies[slot]
             # uniform layers and the plate only scale the beam (:463, :478-480)
             en.intensity_membrane = i0 * np.exp(-2 * k * mem_ub) * plate
             en.intensity_propag = i0 * plate
@@ -198,36 +197,79 @@ class ImageFormation:
                     dst[m].thickness, dst[m].grad_obj, dst[m].grad_ref, dst[m].atten = t.data_ptr(), go, gr, at
                     keep.append(t)
             en.n_hop1, en.n_hop2, en.n_propag = len(hop1), len(hop2), len(prop)
-            en.close_bin = 1 if energy > s.thresholds[ibin] - s.energy_sampling / 2 else 0    # :501
-            if en.close_bin:
-                ibin += 1
-                if ie + 1 < n_e:
-                    bin_starts.add(ie + 1)
-        fwhm = s.effective_source_fwhm()
+            en.close_bin = 1 if ie in closing else 0
+        return energies, keep
+
+    def _rt_job(self, scene, energies, first, sequence):
+        fwhm = scene.effective_source_fwhm()
         src = self._gauss(fwhm / 2.355) if fwhm != 0 else None
-        psf = self._gauss(s.psf_sigma) if s.psf_sigma != 0 else None
+        psf = self._gauss(scene.psf_sigma) if scene.psf_sigma != 0 else None
+        if len(energies) > self.means.numel():
+            self.means = torch.zeros(len(energies), device=self.device, dtype=torch.float64)
         job = abi.RtJob()
         job.nx, job.ny, job.oversampling, job.det_x, job.det_y = self.nx, self.ny, self.os, self.det_x, self.det_y
-        job.first_point, job.n_energies, job.energies_host = int(first), n_e, energies
+        job.first_point, job.n_energies, job.energies_host = int(first), len(energies), energies
         job.i_bs = self.i_bs.data_ptr()
         job.acc_sample, job.acc_ref = self.acc["sample"].data_ptr(), self.acc["reference"].data_ptr()
         job.acc_propag, job.acc_white = self.acc["propag"].data_ptr(), self.acc["white"].data_ptr()
         job.means, job.detect_work = self.means.data_ptr(), self.work.data_ptr()
         job.src_kernel, job.src_half = (src.data_ptr(), (src.numel() - 1) // 2) if src is not None else (None, 0)
         job.psf_kernel, job.psf_half = (psf.data_ptr(), (psf.numel() - 1) // 2) if psf is not None else (None, 0)
-        job.noise, job.seed, job.sequence = int(self.poisson), self.seed, ((sequence_base + point_num) << 16)
+        job.noise, job.seed, job.sequence = int(self.poisson), self.seed, sequence
+        job.flag = self.flag.data_ptr()
+        return job, (src, psf)
+
+    @staticmethod
+    def sequence(point_num, sequence_base=0):
+        """Poisson stream id of a position; image k of bin b draws from sequence + 4b + k."""
+        return (sequence_base + point_num) << 16
+
+    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True):
+        """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526) as one library
+        call (paresis_rt_run).
+
+        Returns a dict of device tensors [nbins, det_x, det_y]: sample, reference (+ propag, white
+        at position 0; absent keys are all-zero images), plus ``mean_energy`` = (sum E*mean,
+        sum mean) of Experiment.py:485-486."""
+        s = scene
+        first = point_num == 0
+        bins = self.bins(s)
+        nbins, n_e = len(s.thresholds), len(s.spectrum)
+        out = self._new_outputs(nbins, first)
+        wd = first and want_displacement
+        if wd and self.dx_pad is None:
+            self.dx_pad = torch.empty((self.nx + 30, self.ny + 30), device=self.device, dtype=torch.float32)
+            self.dy_pad = torch.empty_like(self.dx_pad)
+        closing = {b[-1] for b in bins[:nbins]}
+        energies, keep = self._rt_energies(s, list(range(n_e)), closing)
+        job, keep2 = self._rt_job(s, energies, first, self.sequence(point_num, sequence_base))
         job.out_sample, job.out_ref = out["sample"].data_ptr(), out["reference"].data_ptr()
         if first:
             job.out_propag, job.out_white = out["propag"].data_ptr(), out["white"].data_ptr()
         if wd:
             job.dx_pad, job.dy_pad = self.dx_pad.data_ptr(), self.dy_pad.data_ptr()
-        job.flag = self.flag.data_ptr()
-        launches = n_e * (4 if first else 3) + ibin * (5 if first else 2)
+        launches = n_e * (4 if first else 3) + len(closing) * (5 if first else 2)
         abi.rt_run(job, launches, probe)
         if want_mean:
-            out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
+            starts = {b[0] for b in bins}
+            out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], starts)
             self.check_flag()
         return out
+
+    def accumulate_rt(self, scene, point_num, indices):
+        """The energies ``indices`` (all of ONE detector bin) of a position, without the detector:
+        leaves the partial sums in ``self.acc`` and returns the per-energy means of the reference
+        beam (device float64 tensor, len(indices)).  Used when a bin's energies are spread over
+        several GPUs (shard.py)."""
+        first = point_num == 0
+        energies, keep = self._rt_energies(scene, list(indices), closing=set())
+        job, keep2 = self._rt_job(scene, energies, first, 0)
+        dummy = torch.empty(1, device=self.device, dtype=torch.float32)
+        job.out_sample = job.out_ref = job.out_propag = job.out_white = dummy.data_ptr()
+        abi.rt_run(job, len(indices) * (4 if first else 3))
+        running = self.means[:len(indices)].clone()
+        running[1:] -= self.means[:len(indices) - 1]
+        return running
 
     # ------------------------------------------------------------------ Fresnel
     def _reset(self, n_energies):

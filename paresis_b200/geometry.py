@@ -81,43 +81,54 @@ def from_host(array):
 
 # ---------------------------------------------------------------------------- membrane
 _MEMBRANE_FILE = "Samples/Membranes/CuSn.txt"
-_sphere_cache = {}
+_host_tables = {}     # parsed + rescaled + tiled sphere lists, keyed by file identity and geometry
+_device_tables = {}   # their device copies
+
+
+def drop_device_tables():
+    """Forget the device copies (the next position uploads the sphere list again)."""
+    _device_tables.clear()
 
 
 def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
     """getMembraneFromFile.py:84-124: load, rescale to the wanted mean radius, move the origin to
-    the top-left corner, tile along x then y until the list covers the field of view."""
+    the top-left corner, tile along x then y until the list covers the field of view.
+    The reference re-reads the file at every membrane position; here the parsed list is cached on
+    the host (keyed by the file's identity) and on the device."""
     st = os.stat(path)
-    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size, mean_radius, dim_x, dim_y, pix, torch.cuda.current_device())
-    if key in _sphere_cache:
-        return _sphere_cache[key]
-    if path.split('/')[-1] != 'CuSn.txt':
-        raise Exception("Enter segmented membrane size ")                               # :90
-    corr = mean_radius / 12.8
-    ext_x = int(np.floor(8102)) * corr + mean_radius
-    ext_y = int(np.floor(9740)) * corr + mean_radius
-    with open(path) as fh:
-        tab = np.asarray(json.load(fh), dtype=np.float64) * corr
-    tab[:, 1] += ext_x / 2
-    tab[:, 0] += ext_y / 2
-    base, step = tab.copy(), ext_x
-    while ext_x / pix - dim_x < 0:
-        print("segmented membrane too small: proceeding with stitching along x")
-        shifted = base.copy()
-        shifted[:, 1] += ext_x
-        tab = np.concatenate((tab, shifted), axis=0)
-        ext_x += step
-    base, step = tab.copy(), ext_y
-    while ext_y / pix - dim_y < 0:
-        print("segmented membrane too small: proceeding with stitching along y")
-        shifted = base.copy()
-        shifted[:, 0] += ext_y
-        tab = np.concatenate((tab, shifted), axis=0)
-        ext_y += step
-    dev_tab = transfer.upload(tab, torch.float64, device())
-    _sphere_cache.clear()
-    _sphere_cache[key] = (dev_tab, ext_x, ext_y)
-    return _sphere_cache[key]
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size, mean_radius, dim_x, dim_y, pix)
+    if key not in _host_tables:
+        if path.split('/')[-1] != 'CuSn.txt':
+            raise Exception("Enter segmented membrane size ")                           # :90
+        corr = mean_radius / 12.8
+        ext_x = int(np.floor(8102)) * corr + mean_radius
+        ext_y = int(np.floor(9740)) * corr + mean_radius
+        with open(path) as fh:
+            tab = np.asarray(json.load(fh), dtype=np.float64) * corr
+        tab[:, 1] += ext_x / 2
+        tab[:, 0] += ext_y / 2
+        base, step = tab.copy(), ext_x
+        while ext_x / pix - dim_x < 0:
+            print("segmented membrane too small: proceeding with stitching along x")
+            shifted = base.copy()
+            shifted[:, 1] += ext_x
+            tab = np.concatenate((tab, shifted), axis=0)
+            ext_x += step
+        base, step = tab.copy(), ext_y
+        while ext_y / pix - dim_y < 0:
+            print("segmented membrane too small: proceeding with stitching along y")
+            shifted = base.copy()
+            shifted[:, 0] += ext_y
+            tab = np.concatenate((tab, shifted), axis=0)
+            ext_y += step
+        _host_tables.clear()
+        _device_tables.clear()
+        _host_tables[key] = (np.ascontiguousarray(tab), ext_x, ext_y)
+    tab, ext_x, ext_y = _host_tables[key]
+    dkey = key + (torch.cuda.current_device(),)
+    if dkey not in _device_tables:
+        _device_tables[dkey] = transfer.upload(tab, torch.float64, device())
+    return _device_tables[dkey], ext_x, ext_y
 
 
 def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):

@@ -1,0 +1,92 @@
+"""Sharding the (energy x membrane position) units of a simulation over GPUs.
+
+Positions are independent (each has its own membrane map and output files, main.py:63-110):
+``positions_of`` just deals them out, no communication.  Energies of one detector bin share an
+accumulator (Experiment.py:482-483): each rank forms its partial sums, applies the LINEAR part
+of the detector (blur + bin-down, noise off) and the ranks add those detector-resolution images
+with one NCCL reduction per bin; the Poisson draw follows the sum, on the owner rank, with the
+same counter-based stream a single GPU would use, so the shard layout does not change the
+statistics.  One process per GPU, ``torch.distributed`` (NCCL over NVLink; gloo for CPU tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi as abi
+from .engine import IMAGES
+
+
+def positions_of(n_positions, rank, world):
+    """Round-robin membrane positions of a rank (rank 0 gets position 0 and its extra images)."""
+    return list(range(rank, n_positions, world))
+
+
+def energies_of(indices, rank, world):
+    """Round-robin share of one detector bin's spectrum indices."""
+    return list(indices[rank::world])
+
+
+def reduce_images(stack, owner=0, group=None):
+    """Sum per-rank partial images onto ``owner`` (in place).  ``stack`` is any float tensor."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(stack, dst=owner, op=dist.ReduceOp.SUM, group=group)
+    return stack
+
+
+def combine_means(values, indices, n_total, group=None):
+    """Per-energy reference means computed by different ranks -> one vector on every rank."""
+    full = torch.zeros(n_total, dtype=torch.float64, device=values.device)
+    if len(indices):
+        full[torch.as_tensor(list(indices), device=values.device)] = values
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
+def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, sequence_base=0):
+    """One membrane position with the spectrum spread over the ranks of ``group``.
+
+    Every rank calls this with the same scene.  Returns, on ``owner``, the dict that
+    ``ImageFormation.compute_rt`` returns (device tensors + mean_energy); None elsewhere."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    first = point_num == 0
+    bins = engine.bins(scene)[:len(scene.thresholds)]
+    n_e = len(scene.spectrum)
+    count = 4 if first else 2
+    out = engine._new_outputs(len(bins), first) if rank == owner else None
+    means = torch.zeros(n_e, dtype=torch.float64, device=engine.device)
+    fwhm = scene.effective_source_fwhm()
+    src = engine._gauss(fwhm / 2.355) if fwhm != 0 else None
+    psf = engine._gauss(scene.psf_sigma) if scene.psf_sigma != 0 else None
+    partial = torch.zeros((count, engine.det_x, engine.det_y), device=engine.device, dtype=torch.float32)
+    for b, indices in enumerate(bins):
+        mine = energies_of(indices, rank, world)
+        partial.zero_()
+        if mine:
+            means[torch.as_tensor(mine, device=engine.device)] = engine.accumulate_rt(scene, point_num, mine)
+            if first:   # the white field is the incident beam itself: fill it with this rank's share
+                white = sum(scene.mean_shot_count / scene.os ** 2 * scene.spectrum[i][1] *
+                            scene.common_factor(scene.spectrum[i][0]) * scene.plate_factor(scene.spectrum[i][0]) for i in mine)
+                abi.fill(engine.acc["white"], white)
+            for k, name in enumerate(IMAGES[:count]):
+                # the linear part of the detector before the exchange: detector-resolution images travel
+                abi.detect_counts(engine.acc[name], engine.os, engine.det_x, engine.det_y, src, psf, engine.work,
+                                  partial[k], False)
+        reduce_images(partial, owner, group)
+        if rank == owner:
+            seq = engine.sequence(point_num, sequence_base) + 4 * b
+            for k, name in enumerate(IMAGES[:count]):
+                if engine.poisson:
+                    abi.poisson(partial[k], out[name][b], engine.seed, seq + k)
+                else:
+                    out[name][b].copy_(partial[k])
+    if world > 1:
+        dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
+    if rank != owner:
+        return None
+    m = means.cpu().numpy()
+    energies = np.array([e for e, _ in scene.spectrum])
+    out["mean_energy"] = (float(np.dot(m, energies)), float(m.sum()))
+    engine.check_flag()
+    return out

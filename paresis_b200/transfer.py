@@ -5,12 +5,36 @@ pinned allocator recycles the block once the array is garbage collected), filled
 asynchronous copy on a dedicated copy stream.  ``bytes_d2h`` / ``bytes_h2d`` count what crossed
 PCIe through this module (bench.py reports them).
 """
+import weakref
+
 import numpy as np
 import torch
 
 bytes_d2h = 0
 bytes_h2d = 0
 _copy_streams = {}
+
+# Pinned staging buffers are expensive to create (page locking: ~50 us per MiB), so they are
+# recycled: a buffer goes back to its pool when the numpy array handed to the caller -- and every
+# view of it -- has been garbage collected.
+_pool = {}
+pinned_allocs = 0
+
+
+def _pinned(shape, dtype):
+    global pinned_allocs
+    key = (tuple(shape), dtype)
+    free = _pool.setdefault(key, [])
+    if free:
+        return free.pop()
+    pinned_allocs += 1
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def _release(key, tensor):
+    free = _pool.setdefault(key, [])
+    if len(free) < 8:
+        free.append(tensor)
 
 
 def _copy_stream(device):
@@ -28,7 +52,7 @@ class Pending:
         if dtype is not None and tensor.dtype != dtype:
             tensor = tensor.to(dtype)               # cast on the device, on the producing stream
         self._src = tensor                          # keep alive until the copy is done
-        self.host = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+        self.host = _pinned(tensor.shape, tensor.dtype)
         ready = torch.cuda.Event()
         ready.record()
         stream = _copy_stream(tensor.device)
@@ -42,7 +66,10 @@ class Pending:
     def wait(self):
         self.done.synchronize()
         self._src = None
-        return self.host.numpy()
+        host, self.host = self.host, None
+        arr = host.numpy()
+        weakref.finalize(arr, _release, (tuple(host.shape), host.dtype), host)
+        return arr
 
 
 def fetch(tensor, dtype=None):
