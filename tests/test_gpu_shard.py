@@ -42,7 +42,9 @@ def test_world1_matches_single_call(noise):
             a, b = got[k].cpu().numpy(), ref[k].cpu().numpy()
             assert a.shape == b.shape == (2, 96, 128)
             if noise:
-                assert np.array_equal(a, b), k          # same expectation bits, same Philox stream
+                # same Philox stream; the expectations agree to an ulp (fp32 REDs commit in any order), so
+                # at most a handful of draws sitting exactly on a decision boundary may move
+                assert np.mean(a != b) < 2e-3 and rel_l2(a, b) < 1e-3, k
             else:
                 assert rel_l2(a, b) < 1e-6, k
         assert np.allclose(got["mean_energy"], ref["mean_energy"], rtol=1e-9)
