@@ -39,13 +39,14 @@ METRIC = "speckle_image_sets_per_s"
 UNIT = "image-sets/s"
 WORKLOAD = "2048^2 grid (detector 1024^2 x os 2), mono 52 keV, 20 membrane positions, RayT, PSF 1.2 px + Poisson"
 
-# algorithmic bytes per study pixel (fp32), SURVEY.md section 8(d) / DESIGN.md "Kernels"
+# algorithmic bytes per LAUNCH (fp32), SURVEY.md section 8(d) / DESIGN.md "Kernels": n study pixels, det detector pixels
 ALG_BYTES = {
     "raster_spheres": lambda n, det: 4.0 * n,                 # write the thickness map once
     "refract_membrane_hop": lambda n, det: 8.0 * n,           # read t_m, write I_bs
     "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
-    "detect": lambda n, det: 4.0 * n + 4.0 * det,             # read the image, write detector counts (Poisson fused)
+    "detect": lambda n, det: 2 * (4.0 * n + 4.0 * det),       # sample + reference images in one launch: read, write counts
 }
+SLOTS = 2   # positions in flight (paresis_rt_run_positions deals them over this many streams)
 
 
 def config_dict(**extra):
@@ -228,29 +229,28 @@ def run_gpu(args):
     det = int(exp.myDetector.det_param["myDimensions"][0])
     eng = exp._get_engine()
     mem = exp.myMembrane
-    grains = torch.empty((n, n), device="cuda", dtype=torch.float32)
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda", dtype=torch.float32)
-    thresholds = None
+    plan = geometry.MembranePlan(mem, n, n, mem.membranePixelSize)
+    thresholds = list(exp._open_bins(0))
+    exp.myDetector.det_param["myBinsThersholds"] = []
+    scene = exp._scene(thresholds, per_position_membrane=True)
+    points = list(range(POSITIONS))
+    state = {"buffers": None}
 
-    def device_job(step, probe_label=None, events=None):
-        """20 positions with everything resident in HBM; results stay on the device."""
-        nonlocal thresholds
+    def device_job(step, probe_label=None, events=None, slots=None):
+        """20 positions in one library call, everything resident in HBM; results stay on the device."""
         np.random.seed((10_000 * rank + step) % (2 ** 32))
+        offsets = [plan.draw_offsets() for _ in points]         # the reference's randint draws, in its order
+        pe = None
+        if probe_label is not None:
+            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in points]
+            events.extend(pe)
         with abi.on_stream():
-            for point in range(POSITIONS):
-                geom, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, point, mem.myPMMAThickness, out=grains)
-                mem.myGeometry = geom
-                if thresholds is None:
-                    thresholds = list(exp._open_bins(0))
-                    exp.myDetector.det_param["myBinsThersholds"] = []
-                scene = exp._scene(thresholds)
-                probe = None
-                if probe_label in abi.PROBE:
-                    probe = (probe_label, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                    events.append(probe[1:])
-                eng.compute_rt(scene, point, want_displacement=False, sequence_base=step * POSITIONS, probe=probe,
-                               want_mean=False)
-        eng.check_flag()
+            res = eng.compute_rt_positions(scene, plan, offsets, points, sequence_base=step * POSITIONS,
+                                           n_slots=slots or args.slots, probe_label=probe_label, probe_events=pe,
+                                           buffers=state["buffers"])
+        state["buffers"] = res["buffers"]
+        return res
 
     def api_job(step):
         """The same job through the reference-facing API: host results, membrane map copied back."""
@@ -276,6 +276,7 @@ def run_gpu(args):
     # ---- per-kernel shares (untimed, after a warm-up): which kernel dominates the step?
     device_job(-1)
     torch.cuda.synchronize()
+    eng.check_flag()
     shares = profile_kernels(abi, device_job, torch)
     dominant = max(shares, key=lambda k: shares[k]["ms_per_step"])
     k_events = []
@@ -285,8 +286,6 @@ def run_gpu(args):
     sampler.start()
     for w in range(args.warmup):
         device_job(1000 + w)
-    abi.profile_only = dominant if dominant not in abi.PROBE else None
-    abi.profile_events = []
     barrier()
     sampler.mark()
     launches0 = abi.launches
@@ -302,8 +301,7 @@ def run_gpu(args):
     clocks = sampler.stop()
     launches = abi.launches - launches0
     dev_s = sum(a.elapsed_time(b) for a, b in step_events) * 1e-3
-    k_events = k_events + abi.profile_events
-    abi.profile_only = None
+    eng.check_flag()
     k_ms = [a.elapsed_time(b) for a, b in k_events]
     t = torch.tensor([dev_s], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -342,14 +340,17 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": config_dict(l2="flushed between timed steps (256 MiB write, outside the per-step events)",
                                   timing="CUDA events per step on the launching stream, max over ranks",
-                                  wall_ms_per_step=wall / args.steps * 1e3),
+                                  wall_ms_per_step=wall / args.steps * 1e3, positions_in_flight=args.slots),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "pinned_buffers_allocated": transfer.pinned_allocs},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "alg_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_timed": len(k_ms)},
+                         "alg_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_timed": len(k_ms),
+                         "note": "timed live in the timed region with %d positions in flight (kernels of neighbouring "
+                                 "positions share the SMs); kernel_shares holds the same kernels timed one position at a time"
+                                 % args.slots},
             "kernel_shares": shares,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -360,23 +361,18 @@ def run_gpu(args):
 
 
 def profile_kernels(abi, job, torch):
-    """Untimed jobs with CUDA events around one kernel class at a time: ms per step and per launch.
-    (raster: events around the library call; the kernels inside paresis_rt_run: its probe.)"""
+    """Untimed jobs, one position in flight, with CUDA events around one kernel class at a time (the probe of
+    paresis_rt_run_positions): ms per launch and per 20-position step."""
     out = {}
-    abi.profile_only, abi.profile_events = "raster_spheres", []
-    job(-2)
-    torch.cuda.synchronize()
-    v = [a.elapsed_time(b) for a, b in abi.profile_events]
-    abi.profile_only, abi.profile_events = None, []
-    out["raster_spheres"] = {"ms_per_step": float(np.sum(v)), "ms_per_launch": float(np.mean(v)), "launches": len(v)}
-    per_position = {"refract_membrane_hop": 1, "refract_sample_ref_hop": 1, "detect": 2}
-    for k, label in enumerate(abi.PROBE):
+    launches_per_step = {"raster_spheres": POSITIONS, "refract_membrane_hop": POSITIONS + 1,
+                         "refract_sample_ref_hop": POSITIONS, "detect": POSITIONS}
+    for k, label in enumerate(("raster_spheres", "refract_membrane_hop", "refract_sample_ref_hop", "detect")):
         ev = []
-        job(-3 - k, label, ev)
+        job(-3 - k, label, ev, slots=1)
         torch.cuda.synchronize()
-        v = [a.elapsed_time(b) for a, b in ev]
-        launches = per_position[label] * len(v) + (3 if label == "detect" else 1 if label == "refract_membrane_hop" else 0)
-        out[label] = {"ms_per_step": float(np.mean(v)) * launches, "ms_per_launch": float(np.mean(v)), "launches": launches}
+        v = [a.elapsed_time(b) for a, b in ev][1:]      # position 0 carries the extra images: steady state only
+        out[label] = {"ms_per_step": float(np.mean(v)) * launches_per_step[label], "ms_per_launch": float(np.mean(v)),
+                      "launches": launches_per_step[label]}
     return out
 
 
@@ -387,6 +383,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=SLOTS, help="membrane positions in flight on the GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,6 +98,26 @@ int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
                            float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
                            int nx, int ny, int margin, int* flag, paresis_stream stream);
 
+/* The same kernel with the bookkeeping the per-position pipeline hangs on it, so that a membrane
+ * position needs no separate zero-fill or reduction launches:
+ *   zero_fill[k]  : [nx][ny] buffers set to 0, pixel by pixel (the accumulators the NEXT hop scatters into);
+ *   clear_input   : intensity_in is zeroed once read (it is the scatter target of the next energy);
+ *   zero_scalar   : *zero_scalar = 0 (the sum slot a later launch adds to);
+ *   sum_ref       : *sum_ref += everything the reference beam deposits inside the image
+ *                   (= nx*ny * np.mean(intensityReferenceBeforeDetection), Experiment.py:485-486). */
+typedef struct {
+    float* zero_fill[3];
+    int clear_input;
+    double* zero_scalar;
+    double* sum_ref;
+} paresis_refract_extras;
+
+int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform,
+                              const paresis_layer* layers_host, int n_layers,
+                              float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
+                              int nx, int ny, int margin, int* flag,
+                              const paresis_refract_extras* extras_host, paresis_stream stream);
+
 /* AnalyticalSample.setWaveRT as a stand-alone call (Sample.py:285-351, no dark-field branch):
  * I_out = I_in * exp(-sum atten_m t_m); phi_out = phi_in - sum phase_m t_m (phase_m = k delta_m).
  * phi_in may be NULL (0).  n = pixels. */
@@ -126,9 +146,11 @@ typedef struct {
     int first_point;           /* membrane position 0: propagation and white images too (:488, :510-514) */
     int n_energies;
     const paresis_rt_energy* energies_host;
-    float* i_bs;               /* [nx][ny] scratch: intensity in the object plane */
-    float* acc_sample; float* acc_ref; float* acc_propag; float* acc_white;   /* [nx][ny] accumulators */
-    double* means;             /* [n_energies]: mean of acc_ref after each energy (:485-486) */
+    float* i_bs;               /* [nx][ny] scratch: intensity in the object plane.  Must be ALL ZERO on entry unless
+                                  i_bs_dirty is set; it is all zero again when the job has run. */
+    float* acc_sample; float* acc_ref; float* acc_propag; float* acc_white;   /* [nx][ny] accumulators (any content) */
+    double* means;             /* [n_energies]: SUM over the image of the reference beam of each energy; divide by
+                                  nx*ny for np.mean(intensityReferenceBeforeDetection) (:485-486).  May be NULL. */
     float* detect_work;        /* see paresis_detect_counts; may be NULL for ordinary kernel sizes */
     const float* src_kernel; int src_half;
     const float* psf_kernel; int psf_half;
@@ -137,11 +159,46 @@ typedef struct {
     float* dx_pad; float* dy_pad;   /* optional [(nx+30)][(ny+30)]: Dx, Dy of the sample-only beam, last energy (:492) */
     int* flag;
     /* optional timing probe: cudaEvent_t pair recorded around one kernel of the first energy / bin
-     * (1 = membrane hop, 2 = sample+reference hop, 3 = detector of the sample image); 0 = off */
+     * (1 = membrane hop, 2 = sample+reference hop, 3 = detector launch of the first bin); 0 = off */
     int probe; void* probe_start; void* probe_end;
+    int i_bs_dirty;            /* i_bs holds garbage: zero it first (one extra memset) */
 } paresis_rt_job;
 
 int paresis_rt_run(const paresis_rt_job* job_host, paresis_stream stream);
+
+/* Many membrane positions in ONE call: for each position, rasterise its membrane
+ * (paresis_raster_spheres) and run the per-energy pipeline (paresis_rt_run), positions dealt
+ * round-robin over `n_slots` scratch sets, each on its own stream, so that consecutive positions
+ * overlap on the GPU (positions are independent: main.py:63-110).  `stream` is the caller's
+ * stream: every slot stream first waits for it, and it waits for every slot stream at the end.
+ *
+ * `job_host` is the template of paresis_rt_run: its scratch / output / sequence / first_point /
+ * probe fields are ignored (they come from the slot and the position); a hop layer whose
+ * `thickness` is NULL stands for "the membrane map of this position". */
+typedef struct {
+    const int64_t* offsets_host;   /* [n_layers][2]: the np.random.randint draws of this position (x, y) */
+    float* thickness;              /* [nx][ny] out: membrane grain map, metres */
+    float* out_sample; float* out_ref; float* out_propag; float* out_white;   /* [n_bins][det_x][det_y] */
+    double* means;                 /* [n_energies] or NULL */
+    uint64_t sequence;
+    int first_point;
+    void* probe_start; void* probe_end;   /* optional cudaEvent_t pair for job_host->probe (4 = the membrane raster) */
+} paresis_rt_position;
+
+typedef struct {
+    float* i_bs; float* acc_sample; float* acc_ref; float* acc_propag; float* acc_white;   /* as in paresis_rt_job */
+    void* raster_work; size_t raster_work_bytes;
+    paresis_stream stream;
+    int i_bs_dirty;                /* in/out: cleared once the slot has run a position */
+} paresis_rt_slot;
+
+typedef struct {
+    const double* spheres; int n_spheres; double pix_um; int n_layers; int margin;   /* see paresis_raster_spheres */
+} paresis_membrane;
+
+int paresis_rt_run_positions(const paresis_rt_job* job_host, const paresis_membrane* membrane_host,
+                             const paresis_rt_position* positions_host, int n_positions,
+                             paresis_rt_slot* slots_host, int n_slots, paresis_stream stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fresnel model
@@ -198,6 +255,15 @@ int paresis_detect_counts(const float* image, int nx, int ny, int oversampling, 
                           const float* src_kernel, int src_half, const float* psf_kernel, int psf_half,
                           float* work, float* out, int noise, uint64_t seed, uint64_t sequence,
                           paresis_stream stream);
+
+/* The same for up to 4 images of one detector (sample, reference, propagation, white:
+ * Experiment.py:503-514 calls detection() once per image) in a single launch; image k draws its
+ * noise from sequences_host[k]. */
+int paresis_detect_counts_multi(const float* const* images_host, float* const* outs_host,
+                                const uint64_t* sequences_host, int n_images, int nx, int ny, int oversampling,
+                                int det_x, int det_y, const float* src_kernel, int src_half,
+                                const float* psf_kernel, int psf_half, float* work, int noise, uint64_t seed,
+                                paresis_stream stream);
 
 /* rs.poisson(detectedImage) -- Detector.py:113-115.  Counter-based Philox4x32-10: the draw
  * for pixel p depends only on (seed, sequence, p), so results do not depend on launch shape

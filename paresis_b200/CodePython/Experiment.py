@@ -212,7 +212,14 @@ class Experiment:
             arg += 2 * k * self._lookup(obj.beta[m]).get(energy, 0.0) * t
         return float(np.exp(-arg))
 
-    def _scene(self, thresholds):
+    def _membrane_layers_per_position(self):
+        """The segmented membrane as a batched scene sees it: the grain map is rasterised per position by
+        the library (engine.PER_POSITION), the support plate is a uniform layer (getMembraneFromFile.py:168)."""
+        mem = self.myMembrane
+        entries = [engine.PER_POSITION, mem.myPMMAThickness * 1e-6]
+        return [engine.Layer(t, self._lookup(mem.delta[m]), self._lookup(mem.beta[m])) for m, t in enumerate(entries)]
+
+    def _scene(self, thresholds, per_position_membrane=False):
         d, det, src = self.exp_dict, self.myDetector, self.mySource
 
         def common(energy):
@@ -235,7 +242,8 @@ class Experiment:
             det.det_param['myPixelSize'], det.det_param['myPSF'], d['distSourceToMembrane'], d['distMembraneToObject'],
             d['distObjectToDetector'], d['meanShotCount'], src.mySpectrum, src.source_dict["mySize"],
             src.source_dict["myEnergySampling"], thresholds,
-            self._layers(self.myMembrane, materialise=False), self._layers(self.mySampleofInterest, materialise=True),
+            self._membrane_layers_per_position() if per_position_membrane else self._layers(self.myMembrane, materialise=False),
+            self._layers(self.mySampleofInterest, materialise=True),
             common_factor=common, plate_factor=plate)
 
     def _get_engine(self):

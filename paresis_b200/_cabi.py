@@ -23,9 +23,10 @@ EXPORTS = (
     "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
     "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_detect_work_floats", "paresis_detect",
-    "paresis_detect_counts",
+    "paresis_detect_counts", "paresis_detect_counts_multi",
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
-    "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run",
+    "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
+    "paresis_refract_layers_ex",
 )
 
 
@@ -58,7 +59,30 @@ class RtJob(ctypes.Structure):
                 ("out_sample", ctypes.c_void_p), ("out_ref", ctypes.c_void_p), ("out_propag", ctypes.c_void_p),
                 ("out_white", ctypes.c_void_p), ("dx_pad", ctypes.c_void_p), ("dy_pad", ctypes.c_void_p),
                 ("flag", ctypes.c_void_p), ("probe", ctypes.c_int), ("probe_start", ctypes.c_void_p),
-                ("probe_end", ctypes.c_void_p)]
+                ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int)]
+
+
+class RtPosition(ctypes.Structure):
+    _fields_ = [("offsets_host", ctypes.POINTER(ctypes.c_int64)), ("thickness", ctypes.c_void_p),
+                ("out_sample", ctypes.c_void_p), ("out_ref", ctypes.c_void_p), ("out_propag", ctypes.c_void_p),
+                ("out_white", ctypes.c_void_p), ("means", ctypes.c_void_p), ("sequence", ctypes.c_uint64),
+                ("first_point", ctypes.c_int), ("probe_start", ctypes.c_void_p), ("probe_end", ctypes.c_void_p)]
+
+
+class RtSlot(ctypes.Structure):
+    _fields_ = [("i_bs", ctypes.c_void_p), ("acc_sample", ctypes.c_void_p), ("acc_ref", ctypes.c_void_p),
+                ("acc_propag", ctypes.c_void_p), ("acc_white", ctypes.c_void_p), ("raster_work", ctypes.c_void_p),
+                ("raster_work_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int)]
+
+
+class Membrane(ctypes.Structure):
+    _fields_ = [("spheres", ctypes.c_void_p), ("n_spheres", ctypes.c_int), ("pix_um", ctypes.c_double),
+                ("n_layers", ctypes.c_int), ("margin", ctypes.c_int)]
+
+
+class RefractExtras(ctypes.Structure):
+    _fields_ = [("zero_fill", ctypes.c_void_p * 3), ("clear_input", ctypes.c_int), ("zero_scalar", ctypes.c_void_p),
+                ("sum_ref", ctypes.c_void_p)]
 
 
 class C32(ctypes.Structure):
@@ -89,6 +113,8 @@ def _load():
         "paresis_fresnel_propagate": [vp, vp, vp, vp, C32, vp, vp, vp],
         "paresis_detect": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, vp],
         "paresis_detect_counts": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, ci, u64, u64, vp],
+        "paresis_detect_counts_multi": [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u64), ci, ci, ci, ci, ci, ci, vp, ci,
+                                        vp, ci, vp, ci, u64, vp],
         "paresis_poisson": [vp, vp, sz, u64, u64, vp],
         "paresis_bin_sum": [vp, ci, ci, ci, ci, vp, vp],
         "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp, sz, vp],
@@ -99,6 +125,10 @@ def _load():
         "paresis_mean": [vp, sz, vp, vp],
         "paresis_sum_scaled": [vp, sz, cd, vp, vp],
         "paresis_rt_run": [ctypes.POINTER(RtJob), vp],
+        "paresis_rt_run_positions": [ctypes.POINTER(RtJob), ctypes.POINTER(Membrane), ctypes.POINTER(RtPosition), ci,
+                                     ctypes.POINTER(RtSlot), ci, vp],
+        "paresis_refract_layers_ex": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, vp, vp, ci, ci, ci, vp,
+                                      ctypes.POINTER(RefractExtras), vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -147,7 +177,7 @@ class on_stream:
 
 
 # probe kinds of paresis_rt_run
-PROBE = {"refract_membrane_hop": 1, "refract_sample_ref_hop": 2, "detect": 3}
+PROBE = {"refract_membrane_hop": 1, "refract_sample_ref_hop": 2, "detect": 3, "raster_spheres": 4}
 
 
 def rt_run(job, launches_in_job, probe=None):
@@ -161,6 +191,14 @@ def rt_run(job, launches_in_job, probe=None):
     else:
         job.probe = 0
     _check(lib.paresis_rt_run(ctypes.byref(job), _stream()), "paresis_rt_run")
+    _count(launches_in_job)
+
+
+def rt_run_positions(job, membrane, positions, slots, launches_in_job, probe_label=None):
+    """paresis_rt_run_positions: `positions` / `slots` are ctypes arrays of RtPosition / RtSlot."""
+    job.probe = PROBE[probe_label] if probe_label in PROBE else 0
+    _check(lib.paresis_rt_run_positions(ctypes.byref(job), ctypes.byref(membrane), positions, len(positions), slots,
+                                        len(slots), _stream()), "paresis_rt_run_positions")
     _count(launches_in_job)
 
 
@@ -220,8 +258,9 @@ def refract_phi(intensity, phi, out, distance, energy_kev, magnification, pixel_
 
 
 def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None,
-                   dx_pad=None, dy_pad=None):
-    """layers: list of (thickness tensor, grad_obj, grad_ref, atten)."""
+                   dx_pad=None, dy_pad=None, zero_fill=(), clear_input=False, zero_scalar=None, sum_ref=None):
+    """layers: list of (thickness tensor, grad_obj, grad_ref, atten); the keyword extras are
+    paresis_refract_extras (zero_fill: up to 3 float32 images; zero_scalar / sum_ref: float64 scalars)."""
     n = len(layers)
     arr = (Layer * n)()
     for k, (t, go, gr, at) in enumerate(layers):
@@ -230,10 +269,17 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
         _ptr(t, torch.float32)
     nx, ny = out_obj.shape
     label = "refract_sample_ref_hop" if out_ref is not None else "refract_membrane_hop"
-    _check(_timed(label, lambda: lib.paresis_refract_layers(
+    extras = RefractExtras()
+    for k, z in enumerate(zero_fill):
+        extras.zero_fill[k] = z.data_ptr()
+        _ptr(z, torch.float32)
+    extras.clear_input = 1 if clear_input else 0
+    extras.zero_scalar = zero_scalar.data_ptr() if zero_scalar is not None else None
+    extras.sum_ref = sum_ref.data_ptr() if sum_ref is not None else None
+    _check(_timed(label, lambda: lib.paresis_refract_layers_ex(
         _ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n, _ptr(out_obj, torch.float32),
         _ptr(out_ref, torch.float32), _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
-        _ptr(flag, torch.int32), _stream())), "paresis_refract_layers")
+        _ptr(flag, torch.int32), ctypes.byref(extras), _stream())), "paresis_refract_layers_ex")
     _count()
 
 
@@ -317,6 +363,22 @@ def detect_counts(image, oversampling, det_x, det_y, src_kernel, psf_kernel, wor
         _ptr(image, torch.float32), nx, ny, oversampling, det_x, det_y, _ptr(src_kernel, torch.float32), sh,
         _ptr(psf_kernel, torch.float32), ph, _ptr(work, torch.float32), _ptr(out, torch.float32), 1 if noise else 0,
         int(seed) & (2 ** 64 - 1), int(sequence) & (2 ** 64 - 1), _stream())), "paresis_detect_counts")
+    _count()
+
+
+def detect_counts_multi(images, oversampling, det_x, det_y, src_kernel, psf_kernel, work, outs, noise, seed, sequences):
+    """Up to 4 images of one detector in a single launch (paresis_detect_counts_multi)."""
+    nx, ny = images[0].shape
+    sh = 0 if src_kernel is None else (src_kernel.numel() - 1) // 2
+    ph = 0 if psf_kernel is None else (psf_kernel.numel() - 1) // 2
+    n = len(images)
+    ip = (ctypes.c_void_p * n)(*[_ptr(t, torch.float32) for t in images])
+    op = (ctypes.c_void_p * n)(*[_ptr(t, torch.float32) for t in outs])
+    sq = (ctypes.c_uint64 * n)(*[int(q) & (2 ** 64 - 1) for q in sequences])
+    _check(_timed("detect", lambda: lib.paresis_detect_counts_multi(
+        ip, op, sq, n, nx, ny, oversampling, det_x, det_y, _ptr(src_kernel, torch.float32), sh,
+        _ptr(psf_kernel, torch.float32), ph, _ptr(work, torch.float32), 1 if noise else 0, int(seed) & (2 ** 64 - 1),
+        _stream())), "paresis_detect_counts_multi")
     _count()
 
 

@@ -32,13 +32,33 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "paresis_b200.h")]
+
+
 def build_library(force=False, verbose=False):
+    """Compile every .cu to an object (in parallel, only the stale ones) and link the shared library."""
     if not force and not _stale():
         return LIB
-    flags = [f for f in FLAGS if f != "--use_fast_math=false"]
-    cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
-    if verbose:
-        print(" ".join(cmd))
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")]
+    newest_header = max(os.path.getmtime(h) for h in _headers())
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_header):
+            return obj
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return LIB
 

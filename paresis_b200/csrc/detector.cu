@@ -9,20 +9,10 @@
 // index arithmetic, never materialised.  Everything is fp32, HBM-bound streaming.
 #include <math.h>
 
-#include "common.cuh"
+#include "detector_common.cuh"
+#include "poisson.cuh"
 
 namespace paresis {
-
-constexpr int DET_PAD = 15;     // Detector.py:92
-constexpr int DET_THREADS = 128;
-constexpr int MAX_TAPS = 1024;  // os + 2*half of the composite kernel, kept in shared memory
-
-__device__ __forceinline__ int reflect_index(int q, int n) {
-    // numpy.pad(mode='reflect'): edge sample not repeated; one bounce is enough for pad <= n-1
-    if (q < 0) q = -q;
-    if (q >= n) q = 2 * (n - 1) - q;
-    return q;
-}
 
 __device__ __forceinline__ void build_composite(float* W, const float* __restrict__ g, int half, int os) {
     // W[t], t = d + half, d in [-half, os-1+half]
@@ -127,142 +117,6 @@ bin_sum_kernel(const float* __restrict__ img, int nx, int ny, int s, float* __re
             if (r < nx && c < ny) acc += __ldg(img + (size_t)r * ny + c);
         }
     out[(size_t)a * sy + b] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Poisson noise: Philox4x32-10 counter-based generator + inversion (lam < 10) / PTRS (lam >= 10)
-// ---------------------------------------------------------------------------------------------
-struct Philox {
-    uint32_t c[4], k[2];
-    __device__ __forceinline__ void round() {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-    }
-    __device__ __forceinline__ void generate(uint32_t out[4]) {
-        Philox s = *this;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            s.round();
-            s.k[0] += 0x9E3779B9u;
-            s.k[1] += 0xBB67AE85u;
-        }
-        out[0] = s.c[0]; out[1] = s.c[1]; out[2] = s.c[2]; out[3] = s.c[3];
-    }
-};
-
-__device__ __forceinline__ float u01f(uint32_t x) {
-    return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // 24-bit uniform in (0, 1)
-}
-__device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
-    const uint64_t x = ((uint64_t)hi << 21) ^ (uint64_t)(lo >> 11);   // 53-bit uniform in (0, 1)
-    return ((double)(x & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
-}
-
-// log(k!) for k < 16
-__constant__ float LOG_FACT[16] = {0.f, 0.f, 0.69314718f, 1.79175947f, 3.17805383f, 4.78749174f, 6.57925121f, 8.52516136f,
-                                   10.60460290f, 12.80182748f, 15.10441257f, 17.50230785f, 19.98721450f, 22.55216385f,
-                                   25.19122118f, 27.89927138f};
-
-// log of the Poisson pmf at k for mean lam >= 10, in fp32 without cancellation:
-//   k >= 16: Stirling,  log p = lam * g(x) - log(2 pi k)/2 - 1/(12k) + 1/(360k^3),  x = (k - lam)/lam,
-//            g(x) = x - (1+x) log(1+x)  (series for small x: the two O(lam) terms never meet)
-//   k <  16: -lam + k log(lam) - log(k!) from the table (all terms are small there).
-__device__ __forceinline__ float log_poisson_pmf(float k, float lam) {
-    if (k < 16.f) return -lam + k * logf(lam) - LOG_FACT[(int)k];
-    const float x = (k - lam) / lam;
-    float g;
-    if (fabsf(x) < 0.05f) {
-        const float x2 = x * x;
-        g = x2 * (-0.5f + x * (1.f / 6.f + x * (-1.f / 12.f + x * (0.05f + x * (-1.f / 30.f)))));
-    } else {
-        g = x - (1.f + x) * log1pf(x);
-    }
-    const float ik = 1.f / k;
-    return lam * g - 0.5f * logf(6.28318530718f * k) - ik * (1.f / 12.f - ik * ik * (1.f / 360.f));
-}
-
-// One Poisson variate with mean lam, a pure function of (seed, sequence, pixel).
-//   lam < 10 : inversion by sequential search on one uniform;
-//   lam >= 10: PTRS -- W. Hoermann, "The transformed rejection method for generating Poisson random
-//              variables", Insur. Math. Econ. 12 (1993).  ~86 % of the draws end at the quick
-//              acceptance test; the full test uses the cancellation-free fp32 log-pmf above, so a
-//              warp never waits on fp64 transcendentals.
-__device__ __forceinline__ Philox poisson_stream(uint64_t seed, uint64_t seq, uint64_t pixel) {
-    Philox g;
-    g.c[0] = (uint32_t)pixel;
-    g.c[1] = 0u;
-    g.c[2] = (uint32_t)seq;
-    g.c[3] = (uint32_t)(seq >> 32) ^ (uint32_t)(pixel >> 32);
-    g.k[0] = (uint32_t)seed;
-    g.k[1] = (uint32_t)(seed >> 32);
-    return g;
-}
-
-struct PtrsSetup {
-    float b, a, vr;
-    __device__ __forceinline__ explicit PtrsSetup(float lam) {
-        const float slam = sqrtf(lam);
-        b = 0.931f + 2.53f * slam;
-        a = -0.059f + 0.02483f * b;
-        vr = 0.9277f - 3.6224f / (b - 2.0f);
-    }
-    // k = floor((2a/us + b) U + lam + 0.43): the sum is formed in fp64 so large means keep unit resolution
-    __device__ __forceinline__ float candidate(float lam, float U, float us) const {
-        return (float)floor((double)((2.0f * a / us + b) * U) + (double)lam + 0.43);
-    }
-};
-
-// The cheap part of a draw: everything except PTRS trials that fail the quick acceptance test.
-// Returns true and the variate when it is decided here (lam <= 0, lam < 10, or trial 0 accepted).
-__device__ __forceinline__ bool poisson_quick(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, float& result) {
-    if (!(lam > 0.f)) { result = 0.f; return true; }
-    Philox g = poisson_stream(seed, seq, pixel);
-    uint32_t r[4];
-    g.generate(r);
-    if (lam < 10.f) {
-        const float u = (float)u01d(r[0], r[1]);
-        float p = expf(-lam), F = p;
-        int x = 0;
-        while (u > F && x < 200) {
-            ++x;
-            p *= lam / (float)x;
-            F += p;
-        }
-        result = (float)x;
-        return true;
-    }
-    const PtrsSetup t(lam);
-    const float U = u01f(r[0]) - 0.5f, V = u01f(r[1]);
-    const float us = 0.5f - fabsf(U);
-    result = t.candidate(lam, U, us);
-    return us >= 0.07f && V <= t.vr;
-}
-
-// The full PTRS loop for lam >= 10 (same stream as poisson_quick: trial 0 is replayed first).
-__device__ float poisson_ptrs(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
-    Philox g = poisson_stream(seed, seq, pixel);
-    uint32_t r[4];
-    const PtrsSetup t(lam);
-    const float log_invalpha = logf(1.1239f + 1.1328f / (t.b - 3.4f));
-    for (uint32_t trial = 0; trial < 64; ++trial) {
-        g.c[1] = trial;
-        g.generate(r);
-        const float U = u01f(r[0]) - 0.5f, V = u01f(r[1]);
-        const float us = 0.5f - fabsf(U);
-        const float k = t.candidate(lam, U, us);
-        if (us >= 0.07f && V <= t.vr) return k;
-        if (k < 0.f || (us < 0.013f && V > us)) continue;
-        if (logf(V) + log_invalpha - logf(t.a / (us * us) + t.b) <= log_poisson_pmf(k, lam)) return k;
-    }
-    return floorf(lam + 0.5f);  // unreachable in practice (acceptance > 0.9 per trial)
-}
-
-__device__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
-    float x;
-    if (poisson_quick(lam, seed, seq, pixel, x)) return x;
-    return poisson_ptrs(lam, seed, seq, pixel);
 }
 
 __global__ void __launch_bounds__(256)
@@ -421,7 +275,7 @@ detect_fused_kernel(const float* __restrict__ img, FusedShape s, const float* __
             const int local = queue[2 * qi];
             const float lam = __int_as_float(queue[2 * qi + 1]);
             const size_t p = (size_t)(blockIdx.y * TB + local / TB) * s.det_y + (blockIdx.x * TB + local % TB);
-            out[p] = poisson_ptrs(lam, seed, seq, p);
+            out[p] = poisson_slow(lam, seed, seq, p);
         }
     }
 }
@@ -443,16 +297,8 @@ static int launch_fused(const float* image, const FusedShape& s, const float* gs
 template <bool NOISE>
 static int dispatch_fused(int taps, const float* image, const FusedShape& s, const float* gs, const float* gp, float* out,
                           uint64_t seed, uint64_t seq, size_t smem, cudaStream_t st) {
-    switch (taps) {
-        case 1: return launch_fused<NOISE, 1>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 2: return launch_fused<NOISE, 2>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 3: return launch_fused<NOISE, 3>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 4: return launch_fused<NOISE, 4>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 5: return launch_fused<NOISE, 5>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 6: return launch_fused<NOISE, 6>(image, s, gs, gp, out, seed, seq, smem, st);
-        case 8: return launch_fused<NOISE, 8>(image, s, gs, gp, out, seed, seq, smem, st);
-        default: return launch_fused<NOISE, 0>(image, s, gs, gp, out, seed, seq, smem, st);
-    }
+    (void)taps;   // the sizes PARESIS produces go through detect_tile_kernel; this is the any-size fallback
+    return launch_fused<NOISE, 0>(image, s, gs, gp, out, seed, seq, smem, st);
 }
 
 }  // namespace paresis
@@ -514,31 +360,76 @@ static size_t fused_smem_bytes(const FusedShape& s) {
     return floats * sizeof(float);
 }
 
+static int dispatch_detect_tile(int os, int hs, int hp, PARESIS_DT_ARGS) {
+    switch (os) {
+        case 1: return dispatch_detect_tile_os1(hs, hp, im, n_images, nx, ny, det_x, det_y, gs, gp, noise, seed, st);
+        case 2: return dispatch_detect_tile_os2(hs, hp, im, n_images, nx, ny, det_x, det_y, gs, gp, noise, seed, st);
+        case 3: return dispatch_detect_tile_os3(hs, hp, im, n_images, nx, ny, det_x, det_y, gs, gp, noise, seed, st);
+        case 4: return dispatch_detect_tile_os4(hs, hp, im, n_images, nx, ny, det_x, det_y, gs, gp, noise, seed, st);
+        default: return -1;
+    }
+}
+
+static int detect_args_ok(int nx, int ny, int os, int det_x, int det_y, const float* src_kernel, int src_half,
+                          const float* psf_kernel, int psf_half) {
+    return !(os < 1 || det_x < 1 || det_y < 1 || nx != det_x * os || ny != det_y * os ||
+             DET_PAD * os > nx - 1 || DET_PAD * os > ny - 1 || src_half < 0 || psf_half < 0 ||
+             (src_half > 0 && !src_kernel) || (psf_half > 0 && !psf_kernel) || (long)nx * ny >= (1L << 30));
+}
+
 extern "C" int paresis_detect_counts(const float* image, int nx, int ny, int os, int det_x, int det_y,
                                      const float* src_kernel, int src_half, const float* psf_kernel, int psf_half,
                                      float* work, float* out, int noise, uint64_t seed, uint64_t sequence,
                                      paresis_stream stream) {
-    if (!image || !out || os < 1 || det_x < 1 || det_y < 1 || nx != det_x * os || ny != det_y * os ||
-        DET_PAD * os > nx - 1 || DET_PAD * os > ny - 1 || src_half < 0 || psf_half < 0 ||
-        (src_half > 0 && !src_kernel) || (psf_half > 0 && !psf_kernel) || (long)nx * ny >= (1L << 30)) {
+    if (!image || !out || !detect_args_ok(nx, ny, os, det_x, det_y, src_kernel, src_half, psf_kernel, psf_half)) {
         set_last_error("paresis_detect_counts: bad arguments");
         return PARESIS_ERR_ARG;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* gs = src_half > 0 ? src_kernel : nullptr;
+    const float* gp = psf_half > 0 ? psf_kernel : nullptr;
+    DetImages im{};
+    im.img[0] = image; im.out[0] = out; im.seq[0] = sequence;
+    int rc = dispatch_detect_tile(os, src_half, psf_half, im, 1, nx, ny, det_x, det_y, gs, gp, noise, seed, st);
+    if (rc >= 0) return rc;
     FusedShape s{nx, ny, os, det_x, det_y, src_half, psf_half, TB + 2 * psf_half, (TB + 2 * psf_half) * os + 2 * src_half};
     const size_t smem = fused_smem_bytes(s);
-    cudaStream_t st = (cudaStream_t)stream;
     if (smem > 200 * 1024) {
         // very wide kernels: separable passes through global memory, then the draw in place
         if (!work) { set_last_error("paresis_detect_counts: this kernel size needs the work buffer"); return PARESIS_ERR_ARG; }
-        int rc = paresis_detect(image, nx, ny, os, det_x, det_y, src_kernel, src_half, psf_kernel, psf_half, work, out, stream);
+        rc = paresis_detect(image, nx, ny, os, det_x, det_y, src_kernel, src_half, psf_kernel, psf_half, work, out, stream);
         if (rc != PARESIS_OK || !noise) return rc;
         return paresis_poisson(out, out, (size_t)det_x * det_y, seed, sequence, stream);
     }
-    const float* gs = src_half > 0 ? src_kernel : nullptr;
-    const float* gp = psf_half > 0 ? psf_kernel : nullptr;
     const int taps = os + 2 * src_half;
     return noise ? dispatch_fused<true>(taps, image, s, gs, gp, out, seed, sequence, smem, st)
                  : dispatch_fused<false>(taps, image, s, gs, gp, out, seed, sequence, smem, st);
+}
+
+extern "C" int paresis_detect_counts_multi(const float* const* images_host, float* const* outs_host,
+                                           const uint64_t* sequences_host, int n_images, int nx, int ny, int os,
+                                           int det_x, int det_y, const float* src_kernel, int src_half,
+                                           const float* psf_kernel, int psf_half, float* work, int noise, uint64_t seed,
+                                           paresis_stream stream) {
+    if (!images_host || !outs_host || !sequences_host || n_images < 1 || n_images > DT_MAX_IMAGES ||
+        !detect_args_ok(nx, ny, os, det_x, det_y, src_kernel, src_half, psf_kernel, psf_half)) {
+        set_last_error("paresis_detect_counts_multi: bad arguments (1..%d images)", DT_MAX_IMAGES);
+        return PARESIS_ERR_ARG;
+    }
+    DetImages im{};
+    for (int k = 0; k < n_images; ++k) {
+        if (!images_host[k] || !outs_host[k]) { set_last_error("paresis_detect_counts_multi: null image %d", k); return PARESIS_ERR_ARG; }
+        im.img[k] = images_host[k]; im.out[k] = outs_host[k]; im.seq[k] = sequences_host[k];
+    }
+    int rc = dispatch_detect_tile(os, src_half, psf_half, im, n_images, nx, ny, det_x, det_y, src_half > 0 ? src_kernel : nullptr,
+                                  psf_half > 0 ? psf_kernel : nullptr, noise, seed, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+    for (int k = 0; k < n_images; ++k) {   // unusual kernel sizes: one image at a time
+        rc = paresis_detect_counts(images_host[k], nx, ny, os, det_x, det_y, src_kernel, src_half, psf_kernel, psf_half, work,
+                                   outs_host[k], noise, seed, sequences_host[k], stream);
+        if (rc != PARESIS_OK) return rc;
+    }
+    return PARESIS_OK;
 }
 
 extern "C" int paresis_poisson(const float* expect, float* counts, size_t n, uint64_t seed, uint64_t sequence,

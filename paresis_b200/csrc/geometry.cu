@@ -16,80 +16,120 @@ struct LayerOffsets {
     long long y[MAX_MEMBRANE_LAYERS];
 };
 
-// Two kernels.  cull: one thread per (layer, sphere) candidate tests the reference's acceptance
-// window (:151) and the field of view; a survivor (~3 %) cuts its bounding box (:155-159) into
-// chunks of RASTER_CHUNK cells and appends one work item per chunk to a list in `work`.
-// fill: warps walk that list, so the cost of a rare 100-pixel grain is spread over many warps
-// instead of stalling one block.  Each cell adds 2*sqrt(r^2 - d^2) with REDG.ADD.F32; the
-// cancelling difference r^2 - d^2 stays in fp64.
+// Two kernels, no atomics on the image.
+//   bin:    one thread per (layer, sphere) candidate tests the reference's acceptance window (:151)
+//           and the field of view; a survivor (~3 %) appends its id to the list of every 32 x 32 pixel
+//           tile its bounding box (:155-159) touches.
+//   gather: one block per tile; the tile's spheres are staged in shared memory and every thread sums
+//           the caps over its own four pixels in registers (the cancelling r^2 - d^2 stays in fp64),
+//           then writes them with plain coalesced stores.  The map is written exactly once: no
+//           zero-fill pass, no read-modify-write.
+// A tile whose list overflows RASTER_CAP falls back to scanning all candidates itself (correct,
+// slow, and not reachable with physical membranes: ~6 spheres per tile at the bundled density).
 constexpr int RASTER_THREADS = 256;
-constexpr int RASTER_CHUNK = 512;
+constexpr int RASTER_TILE = 32;
+constexpr int RASTER_CAP = 256;
 
-struct RasterItem {
-    double xf, yf, rad;
-    int x, y, chunk, pad_;
+struct Cap {
+    double xf, yf, r2;       // centre (canvas coordinates) and squared radius, pixels
+    int rlo, rhi, clo, chi;  // bounding box in image coordinates, inclusive (:155-159)
 };
 
-__device__ __forceinline__ void raster_chunk(const RasterItem& h, int lane, int nlanes, double scale_m, int dim_x, int dim_y,
-                                             int margin, float* __restrict__ out) {
-    const int reach = (int)floor(h.rad) + 1;
-    const int w = 2 * reach;
-    const double r2 = h.rad * h.rad;
-    const double ex0 = (double)h.x - h.xf, ey0 = (double)h.y - h.yf;
-    const unsigned magic = 0xffffffffu / (unsigned)w + 1u;   // idx / w == umulhi(idx, magic) for idx < w*w <= 2^20
-    const int r0 = h.x - reach - margin, c0 = h.y - reach - margin;   // canvas -> cropped field of view (:161)
-    const int end = min((h.chunk + 1) * RASTER_CHUNK, w * w);
-    const float two_scale = 2.0f * (float)scale_m;
-    for (int idx = h.chunk * RASTER_CHUNK + lane; idx < end; idx += nlanes) {
-        const int q = (int)__umulhi((unsigned)idx, magic);
-        const int p = idx - q * w;
-        const int r = r0 + q, c = c0 + p;
-        if ((unsigned)r >= (unsigned)dim_x || (unsigned)c >= (unsigned)dim_y) continue;
-        const double ex = (double)(q - reach) + ex0, ey = (double)(p - reach) + ey0;
-        const float diff = (float)(r2 - (ex * ex + ey * ey));
-        if (diff > 0.f) {
-            float inv;   // sqrt(x) = x * rsqrt(x): one MUFU, ~2 ulp, no IEEE fix-up code in the inner loop
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(diff));
-            red_add(out + (size_t)r * dim_y + c, two_scale * (diff * inv));
-        }
-    }
-}
-
-__global__ void __launch_bounds__(RASTER_THREADS)
-raster_cull_kernel(const double* __restrict__ spheres, int n, double pix, double scale_m, LayerOffsets off, int n_layers,
-                   int dim_x, int dim_y, int margin, float* __restrict__ out, int* __restrict__ count,
-                   RasterItem* __restrict__ items, int capacity) {
-    const long long id = (long long)blockIdx.x * RASTER_THREADS + threadIdx.x;
-    if (id >= (long long)n * n_layers) return;
-    const int layer = (int)(id / n), s = (int)(id % n);
+// Sphere `s` of layer `layer`: acceptance test and bounding box.  Returns false when it adds nothing.
+__device__ __forceinline__ bool make_cap(const double* __restrict__ spheres, int s, int layer, double pix, const LayerOffsets& off,
+                                         int dim_x, int dim_y, int margin, Cap& c) {
+    const double rad = spheres[3 * s + 2] / pix;
+    c.xf = spheres[3 * s + 1] / pix - (double)off.x[layer];
+    c.yf = spheres[3 * s + 0] / pix - (double)off.y[layer];
+    c.r2 = rad * rad;
+    const long long x = __double2ll_rn(c.xf), y = __double2ll_rn(c.yf);   // np.round: half to even (:149-150)
+    const long long reach = (long long)floor(rad) + 1;
     const int margin2 = margin / 2;
-    RasterItem h;
-    h.rad = spheres[3 * s + 2] / pix;
-    h.xf = spheres[3 * s + 1] / pix - (double)off.x[layer];
-    h.yf = spheres[3 * s + 0] / pix - (double)off.y[layer];
-    const long long x = __double2ll_rn(h.xf), y = __double2ll_rn(h.yf);   // np.round: half to even (:149-150)
-    const long long reach = (long long)floor(h.rad) + 1;
     const bool accepted = margin2 < x && x < dim_x + margin + margin2 && margin2 < y && y < dim_y + margin + margin2;
     const bool visible = x + reach > margin && x - reach < dim_x + margin && y + reach > margin && y - reach < dim_y + margin;
-    if (!(accepted && visible) || reach > 500) return;   // (a 500-pixel grain would already exceed the canvas margin)
-    h.x = (int)x; h.y = (int)y; h.pad_ = 0;
-    const int cells = (int)(4 * reach * reach);
-    const int chunks = (cells + RASTER_CHUNK - 1) / RASTER_CHUNK;
-    const int base = atomicAdd(count, chunks);
-    for (int k = 0; k < chunks; ++k) {
-        h.chunk = k;
-        if (base + k < capacity) items[base + k] = h;
-        else raster_chunk(h, 0, 1, scale_m, dim_x, dim_y, margin, out);   // list full: do it here, slowly but correctly
-    }
+    if (!(accepted && visible) || reach > 500) return false;   // (a 500-pixel grain would already exceed the canvas margin)
+    // canvas rows x-reach .. x+reach-1 (:155-159), cropped by `margin` (:161)
+    c.rlo = (int)(x - reach) - margin; c.rhi = (int)(x + reach) - 1 - margin;
+    c.clo = (int)(y - reach) - margin; c.chi = (int)(y + reach) - 1 - margin;
+    return true;
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS)
-raster_fill_kernel(const int* __restrict__ count, const RasterItem* __restrict__ items, int capacity, double scale_m,
-                   int dim_x, int dim_y, int margin, float* __restrict__ out) {
-    const int n_items = min(*count, capacity);
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * RASTER_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * RASTER_THREADS) >> 5;
-    for (int e = warp; e < n_items; e += n_warps) raster_chunk(items[e], lane, 32, scale_m, dim_x, dim_y, margin, out);
+raster_bin_kernel(const double* __restrict__ spheres, int n, double pix, LayerOffsets off, int n_layers, int dim_x, int dim_y,
+                  int margin, int tiles_y, int* __restrict__ count, int* __restrict__ entries, int* __restrict__ n_caps,
+                  Cap* __restrict__ caps) {
+    const long long id = (long long)blockIdx.x * RASTER_THREADS + threadIdx.x;
+    if (id >= (long long)n * n_layers) return;
+    Cap c;
+    if (!make_cap(spheres, (int)(id % n), (int)(id / n), pix, off, dim_x, dim_y, margin, c)) return;
+    const int slot_c = atomicAdd(n_caps, 1);     // < n * n_layers = capacity of `caps`
+    caps[slot_c] = c;
+    const int tr0 = max(c.rlo, 0) / RASTER_TILE, tr1 = min(c.rhi, dim_x - 1) / RASTER_TILE;
+    const int tc0 = max(c.clo, 0) / RASTER_TILE, tc1 = min(c.chi, dim_y - 1) / RASTER_TILE;
+    for (int tr = tr0; tr <= tr1; ++tr)
+        for (int tc = tc0; tc <= tc1; ++tc) {
+            const int tile = tr * tiles_y + tc;
+            const int slot = atomicAdd(count + tile, 1);
+            if (slot < RASTER_CAP) entries[(size_t)tile * RASTER_CAP + slot] = slot_c;
+        }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_gather_kernel(const int* __restrict__ n_caps_all, const Cap* __restrict__ caps_all, int dim_x, int dim_y, int margin,
+                     float two_scale, int tiles_y, const int* __restrict__ count, const int* __restrict__ entries,
+                     float* __restrict__ out) {
+    __shared__ Cap caps[RASTER_CAP];
+    __shared__ int n_caps;
+    const int tile = blockIdx.y * tiles_y + blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * RASTER_TILE + 4 * warp;      // this thread: rows r0 .. r0+3, column c
+    const int c = blockIdx.x * RASTER_TILE + lane;
+    const int t_rlo = blockIdx.y * RASTER_TILE, t_rhi = t_rlo + RASTER_TILE - 1;
+    const int t_clo = blockIdx.x * RASTER_TILE, t_chi = t_clo + RASTER_TILE - 1;
+    const int listed = count[tile];
+    const bool overflow = listed > RASTER_CAP;               // then: scan every accepted cap
+    const int total = overflow ? *n_caps_all : listed;
+    const double cd = (double)(c + margin), rd = (double)(r0 + margin);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = 0; base < total; base += RASTER_CAP) {
+        if (threadIdx.x == 0) n_caps = 0;
+        __syncthreads();
+        const int e = base + threadIdx.x;
+        if (e < total) {
+            const Cap cp = caps_all[overflow ? e : entries[(size_t)tile * RASTER_CAP + e]];
+            if (!overflow || (cp.rlo <= t_rhi && cp.rhi >= t_rlo && cp.clo <= t_chi && cp.chi >= t_clo))
+                caps[overflow ? atomicAdd(&n_caps, 1) : threadIdx.x] = cp;
+        }
+        if (!overflow && threadIdx.x == 0) n_caps = min(total - base, RASTER_CAP);
+        __syncthreads();
+        const int m = n_caps;
+        for (int k = 0; k < m; ++k) {
+            const Cap& cp = caps[k];
+            if (cp.rhi < r0 || cp.rlo > r0 + 3) continue;          // warp-uniform: rows of this warp
+            if (c < cp.clo || c > cp.chi) continue;
+            const double ey = cd - cp.yf;
+            const double rem = cp.r2 - ey * ey;
+            const double ex0 = rd - cp.xf;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + q;
+                const double ex = ex0 + (double)q;
+                const float diff = (float)(rem - ex * ex);
+                if (diff > 0.f && r >= cp.rlo && r <= cp.rhi) {
+                    float inv;   // sqrt(x) = x * rsqrt(x): one MUFU, ~2 ulp
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(diff));
+                    acc[q] = fmaf(two_scale, diff * inv, acc[q]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (c < dim_y) {
+        float* o = out + (size_t)r0 * dim_y + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (r0 + q < dim_x) o[(size_t)q * dim_y] = acc[q];
+    }
 }
 
 __global__ void sphere_map_kernel(double rad, double scale_m, int dim_x, int dim_y, float* __restrict__ out) {
@@ -140,9 +180,10 @@ __global__ void cylinder_map_kernel(Affine inv, double rad, double scale_m, int 
 using namespace paresis;
 
 extern "C" size_t paresis_raster_work_bytes(int n_spheres, int n_layers, int dim_x, int dim_y) {
-    (void)n_spheres;
-    const size_t items = (size_t)dim_x * dim_y * (size_t)(n_layers > 0 ? n_layers : 1) / 128 + 65536;
-    return 16 + items * sizeof(RasterItem);
+    const size_t tiles = (size_t)div_up(dim_x, RASTER_TILE) * div_up(dim_y, RASTER_TILE);
+    const size_t cands = (size_t)(n_spheres > 0 ? n_spheres : 0) * (size_t)(n_layers > 0 ? n_layers : 1);
+    // [tile counts + cap counter | tile lists | accepted caps]
+    return ((tiles + 1 + 3) / 4 * 4 + tiles * RASTER_CAP) * sizeof(int) + (cands + 1) * sizeof(Cap);
 }
 
 extern "C" int paresis_raster_spheres(const double* spheres, int n_spheres, double pix_um,
@@ -150,30 +191,36 @@ extern "C" int paresis_raster_spheres(const double* spheres, int n_spheres, doub
                                       int margin, float* thickness_out, void* work, size_t work_bytes,
                                       paresis_stream stream) {
     if (!spheres || !offsets_host || !thickness_out || n_spheres < 0 || n_layers < 1 || n_layers > MAX_MEMBRANE_LAYERS ||
-        dim_x < 1 || dim_y < 1 || margin < 0 || !(pix_um > 0) || !work || work_bytes < 16 + sizeof(RasterItem)) {
-        set_last_error("paresis_raster_spheres: bad arguments (layers 1..%d, work buffer required)", MAX_MEMBRANE_LAYERS);
+        dim_x < 1 || dim_y < 1 || margin < 0 || !(pix_um > 0) || !work ||
+        work_bytes < paresis_raster_work_bytes(n_spheres, n_layers, dim_x, dim_y) || (long long)n_spheres * n_layers >= (1LL << 31)) {
+        set_last_error("paresis_raster_spheres: bad arguments (layers 1..%d, work buffer of paresis_raster_work_bytes required)",
+                       MAX_MEMBRANE_LAYERS);
         return PARESIS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    PARESIS_CUDA(cudaMemsetAsync(thickness_out, 0, sizeof(float) * (size_t)dim_x * dim_y, s));
-    if (n_spheres == 0) return PARESIS_OK;
     LayerOffsets off{};
     for (int l = 0; l < n_layers; ++l) {
         off.x[l] = offsets_host[2 * l];
         off.y[l] = offsets_host[2 * l + 1];
     }
+    const int tiles_x = div_up(dim_x, RASTER_TILE), tiles_y = div_up(dim_y, RASTER_TILE);
+    const size_t tiles = (size_t)tiles_x * tiles_y;
     int* count = (int*)work;
-    RasterItem* items = (RasterItem*)((char*)work + 16);
-    const int capacity = (int)((work_bytes - 16) / sizeof(RasterItem));
-    PARESIS_CUDA(cudaMemsetAsync(count, 0, sizeof(int), s));
+    int* n_caps = count + tiles;
+    int* entries = count + (tiles + 1 + 3) / 4 * 4;
+    Cap* caps = (Cap*)(entries + tiles * RASTER_CAP);
+    PARESIS_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (tiles + 1), s));
     const long long candidates = (long long)n_spheres * n_layers;
-    const int blocks = (int)((candidates + RASTER_THREADS - 1) / RASTER_THREADS);
-    raster_cull_kernel<<<blocks, RASTER_THREADS, 0, s>>>(spheres, n_spheres, pix_um, pix_um * 1e-6, off, n_layers, dim_x,
-                                                          dim_y, margin, thickness_out, count, items, capacity);
-    PARESIS_LAUNCH_CHECK("raster_cull_kernel");
-    raster_fill_kernel<<<148 * 4, RASTER_THREADS, 0, s>>>(count, items, capacity, pix_um * 1e-6, dim_x, dim_y, margin,
-                                                           thickness_out);
-    PARESIS_LAUNCH_CHECK("raster_fill_kernel");
+    if (candidates > 0) {
+        const int blocks = (int)((candidates + RASTER_THREADS - 1) / RASTER_THREADS);
+        raster_bin_kernel<<<blocks, RASTER_THREADS, 0, s>>>(spheres, n_spheres, pix_um, off, n_layers, dim_x, dim_y, margin,
+                                                             tiles_y, count, entries, n_caps, caps);
+        PARESIS_LAUNCH_CHECK("raster_bin_kernel");
+    }
+    raster_gather_kernel<<<dim3(tiles_y, tiles_x), RASTER_THREADS, 0, s>>>(n_caps, caps, dim_x, dim_y, margin,
+                                                                            2.0f * (float)(pix_um * 1e-6), tiles_y, count, entries,
+                                                                            thickness_out);
+    PARESIS_LAUNCH_CHECK("raster_gather_kernel");
     return PARESIS_OK;
 }
 

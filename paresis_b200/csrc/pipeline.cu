@@ -1,17 +1,24 @@
-// One membrane position of the ray-tracing model as ONE library call.
+// Membrane positions of the ray-tracing model as single library calls.
 //
 // Reference: Experiment.computeSampleAndReferenceImages_RT, Experiment.py:407-526 -- the loop over
-// the spectrum (:448) with its three or four refraction hops per energy (:463-498), the running
-// mean of the reference image (:485-486) and the detector call at every bin close (:501-521).
-// The host shim prepares the per-energy scalars in fp64; everything below is kernel launches on
-// one stream, so a position costs one Python -> C transition instead of a dozen.
+// the spectrum (:448) with its three or four refraction hops per energy (:463-498), the mean of the
+// reference image (:485-486) and the detector call at every bin close (:501-521); main.py:63-110 for
+// the loop over membrane positions around it.  The host shim prepares the per-energy scalars in fp64;
+// everything below is kernel launches.
+//
+// Launch sequence of one steady-state position (mono): raster bin + gather, membrane hop, sample +
+// reference hop, detector = 5 kernels and one 16 KB memset.  There are no zero-fill or reduction
+// passes: each hop zero-fills what the next one scatters into, the object hop clears I_bs behind
+// itself and sums the reference beam while it deposits it (paresis_refract_extras).
+#include <vector>
+
 #include "common.cuh"
 
 using namespace paresis;
 
 extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) {
     if (!job || !job->energies_host || job->n_energies < 1 || !job->i_bs || !job->acc_sample || !job->acc_ref ||
-        !job->out_sample || !job->out_ref || !job->means ||
+        !job->out_sample || !job->out_ref ||
         (job->first_point && (!job->acc_propag || !job->acc_white || !job->out_propag || !job->out_white))) {
         set_last_error("paresis_rt_run: incomplete job description");
         return PARESIS_ERR_ARG;
@@ -19,7 +26,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)job->nx * job->ny, nd = (size_t)job->det_x * job->det_y;
     const int margin = 15;   // refractionFileNumba2.py:50
-    PARESIS_CUDA(cudaMemsetAsync(job->means, 0, sizeof(double) * job->n_energies, s));
+    if (job->i_bs_dirty) PARESIS_CUDA(cudaMemsetAsync(job->i_bs, 0, sizeof(float) * n, s));
     bool fresh_bin = true;
     int ibin = 0;
     float white = 0.f;
@@ -33,27 +40,30 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
             set_last_error("paresis_rt_run: energy %d has an empty hop", e);
             return PARESIS_ERR_ARG;
         }
+        // membrane -> object plane (Experiment.py:463-466); a fresh detector bin starts from zero accumulators
+        paresis_refract_extras x1{};
         if (fresh_bin) {
-            PARESIS_CUDA(cudaMemsetAsync(job->acc_sample, 0, sizeof(float) * n, s));
-            PARESIS_CUDA(cudaMemsetAsync(job->acc_ref, 0, sizeof(float) * n, s));
-            if (job->first_point) PARESIS_CUDA(cudaMemsetAsync(job->acc_propag, 0, sizeof(float) * n, s));
+            x1.zero_fill[0] = job->acc_sample;
+            x1.zero_fill[1] = job->acc_ref;
+            x1.zero_fill[2] = job->first_point ? job->acc_propag : nullptr;
             white = 0.f;
             fresh_bin = false;
         }
-        // membrane -> object plane (Experiment.py:463-466)
-        PARESIS_CUDA(cudaMemsetAsync(job->i_bs, 0, sizeof(float) * n, s));
+        x1.zero_scalar = job->means ? job->means + e : nullptr;
         if (e == 0) probe(1, true);
-        int rc = paresis_refract_layers(nullptr, en.intensity_membrane, en.hop1, en.n_hop1, job->i_bs, nullptr, nullptr,
-                                        nullptr, job->nx, job->ny, margin, job->flag, stream);
+        int rc = paresis_refract_layers_ex(nullptr, en.intensity_membrane, en.hop1, en.n_hop1, job->i_bs, nullptr, nullptr,
+                                           nullptr, job->nx, job->ny, margin, job->flag, &x1, stream);
         if (e == 0) probe(1, false);
         if (rc) return rc;
+        // object -> detector: sample beam and reference beam in one pass over I_bs (:469-474), which is
+        // cleared behind the pass; the reference beam is summed on the way (:485-486)
+        paresis_refract_extras x2{};
+        x2.clear_input = 1;
+        x2.sum_ref = job->means ? job->means + e : nullptr;
         if (e == 0) probe(2, true);
-        // object -> detector: sample beam and reference beam in one pass over I_bs (:469-474)
-        rc = paresis_refract_layers(job->i_bs, 0.f, en.hop2, en.n_hop2, job->acc_sample, job->acc_ref, nullptr, nullptr,
-                                    job->nx, job->ny, margin, job->flag, stream);
+        rc = paresis_refract_layers_ex(job->i_bs, 0.f, en.hop2, en.n_hop2, job->acc_sample, job->acc_ref, nullptr, nullptr,
+                                       job->nx, job->ny, margin, job->flag, &x2, stream);
         if (e == 0) probe(2, false);
-        if (rc) return rc;
-        rc = paresis_sum_scaled(job->acc_ref, n, 1.0 / (double)n, job->means + e, stream);   // :485-486 (running)
         if (rc) return rc;
         if (job->first_point) {
             // the sample alone (:490-498); the white field is the incident beam itself
@@ -78,17 +88,98 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
                 rc = paresis_fill(job->acc_white, white, n, stream);
                 if (rc) return rc;
             }
-            for (int k = 0; k < count; ++k) {
-                if (ibin == 0 && k == 0) probe(3, true);
-                rc = paresis_detect_counts(imgs[k], job->nx, job->ny, job->oversampling, job->det_x, job->det_y,
-                                           job->src_kernel, job->src_half, job->psf_kernel, job->psf_half, job->detect_work,
-                                           outs[k] + (size_t)ibin * nd, job->noise, job->seed, seq + k, stream);
-                if (ibin == 0 && k == 0) probe(3, false);
-                if (rc) return rc;
-            }
+            // all images of the bin in one launch (Detector.detection is called once per image, :503-514)
+            const float* in_k[4]; float* out_k[4]; uint64_t seq_k[4];
+            for (int k = 0; k < count; ++k) { in_k[k] = imgs[k]; out_k[k] = outs[k] + (size_t)ibin * nd; seq_k[k] = seq + k; }
+            if (ibin == 0) probe(3, true);
+            rc = paresis_detect_counts_multi(in_k, out_k, seq_k, count, job->nx, job->ny, job->oversampling, job->det_x,
+                                             job->det_y, job->src_kernel, job->src_half, job->psf_kernel, job->psf_half,
+                                             job->detect_work, job->noise, job->seed, stream);
+            if (ibin == 0) probe(3, false);
+            if (rc) return rc;
             ++ibin;
             fresh_bin = true;
         }
+    }
+    return PARESIS_OK;
+}
+
+namespace {
+// fork / join events of the slot streams, created once per process
+struct SlotEvents {
+    cudaEvent_t fork = nullptr;
+    std::vector<cudaEvent_t> join;
+    int ensure(int n) {
+        if (!fork) PARESIS_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        while ((int)join.size() < n) {
+            cudaEvent_t e;
+            PARESIS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            join.push_back(e);
+        }
+        return PARESIS_OK;
+    }
+};
+SlotEvents g_events;
+}  // namespace
+
+extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis_membrane* mem,
+                                        const paresis_rt_position* positions, int n_positions,
+                                        paresis_rt_slot* slots, int n_slots, paresis_stream stream) {
+    if (!job || !mem || !positions || !slots || n_positions < 0 || n_slots < 1 || !job->energies_host || job->n_energies < 1) {
+        set_last_error("paresis_rt_run_positions: bad arguments");
+        return PARESIS_ERR_ARG;
+    }
+    if (n_positions == 0) return PARESIS_OK;
+    int rc = g_events.ensure(n_slots);
+    if (rc) return rc;
+    cudaStream_t main_stream = (cudaStream_t)stream;
+    const int used = n_slots < n_positions ? n_slots : n_positions;
+    PARESIS_CUDA(cudaEventRecord(g_events.fork, main_stream));
+    for (int k = 0; k < used; ++k) PARESIS_CUDA(cudaStreamWaitEvent((cudaStream_t)slots[k].stream, g_events.fork, 0));
+
+    std::vector<paresis_rt_energy> energies(job->energies_host, job->energies_host + job->n_energies);
+    for (int p = 0; p < n_positions; ++p) {
+        const paresis_rt_position& pos = positions[p];
+        paresis_rt_slot& slot = slots[p % n_slots];
+        if (!pos.offsets_host || !pos.thickness) {
+            set_last_error("paresis_rt_run_positions: position %d lacks offsets or a thickness buffer", p);
+            return PARESIS_ERR_ARG;
+        }
+        const bool probe_raster = job->probe == 4 && pos.probe_start && pos.probe_end;
+        if (probe_raster) cudaEventRecord((cudaEvent_t)pos.probe_start, (cudaStream_t)slot.stream);
+        rc = paresis_raster_spheres(mem->spheres, mem->n_spheres, mem->pix_um, pos.offsets_host, mem->n_layers, job->nx,
+                                    job->ny, mem->margin, pos.thickness, slot.raster_work, slot.raster_work_bytes, slot.stream);
+        if (probe_raster) cudaEventRecord((cudaEvent_t)pos.probe_end, (cudaStream_t)slot.stream);
+        if (rc) return rc;
+        // a NULL layer map stands for this position's membrane
+        for (int e = 0; e < job->n_energies; ++e) {
+            const paresis_rt_energy& src = job->energies_host[e];
+            paresis_rt_energy& dst = energies[e];
+            for (int m = 0; m < PARESIS_MAX_LAYERS; ++m) {
+                dst.hop1[m].thickness = src.hop1[m].thickness ? src.hop1[m].thickness : pos.thickness;
+                dst.hop2[m].thickness = src.hop2[m].thickness ? src.hop2[m].thickness : pos.thickness;
+                dst.propag[m].thickness = src.propag[m].thickness ? src.propag[m].thickness : pos.thickness;
+            }
+        }
+        paresis_rt_job j = *job;
+        j.energies_host = energies.data();
+        j.first_point = pos.first_point;
+        j.i_bs = slot.i_bs; j.acc_sample = slot.acc_sample; j.acc_ref = slot.acc_ref;
+        j.acc_propag = slot.acc_propag; j.acc_white = slot.acc_white;
+        j.i_bs_dirty = slot.i_bs_dirty;
+        j.means = pos.means;
+        j.out_sample = pos.out_sample; j.out_ref = pos.out_ref; j.out_propag = pos.out_propag; j.out_white = pos.out_white;
+        j.sequence = pos.sequence;
+        j.probe_start = pos.probe_start; j.probe_end = pos.probe_end;
+        if (!pos.probe_start || !pos.probe_end) j.probe = 0;
+        j.dx_pad = j.dy_pad = nullptr;
+        rc = paresis_rt_run(&j, slot.stream);
+        if (rc) return rc;
+        slot.i_bs_dirty = 0;
+    }
+    for (int k = 0; k < used; ++k) {
+        PARESIS_CUDA(cudaEventRecord(g_events.join[k], (cudaStream_t)slots[k].stream));
+        PARESIS_CUDA(cudaStreamWaitEvent(main_stream, g_events.join[k], 0));
     }
     return PARESIS_OK;
 }

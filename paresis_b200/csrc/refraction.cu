@@ -75,6 +75,14 @@ struct RefractArgs {
     float clamp_x, clamp_y;   // rays with |D| above these are dropped (v2: nx, ny; v1: 1e3)
     int rows;
     int* flag;
+    // pipeline extras (all optional): buffers the NEXT kernel accumulates into are zero-filled here, pixel
+    // by pixel; the input intensity is cleared once read (so the next energy can scatter into it again);
+    // the sum of everything the reference beam deposits inside the image is added to *sum_ref
+    // (= N * mean of the reference image of this energy, Experiment.py:485-486).
+    float* zero[3];
+    bool clear_input;
+    double* sum_ref;
+    double* zero_scalar;
 };
 
 // refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
@@ -116,11 +124,14 @@ refract_kernel(const RefractArgs<T> a) {
         halo[m] = a.map[m] + (size_t)i0 * f.ny + jh;
     }
     const float* irow = HAS_I ? a.I_in + (size_t)i0 * f.ny + jc : nullptr;
-    float vin = HAS_I ? __ldg(irow) : a.I_uniform;
+    // plain loads: with clear_input the same thread stores to this address after reading it
+    float vin = HAS_I ? *irow : a.I_uniform;
 
     Splatter<MODE> sp_obj, sp_ref;
     sp_obj.init(a.out_obj, f.ny, a.flag);
     if (DUAL) sp_ref.init(a.out_ref, f.ny, a.flag);
+    float ref_sum = 0.f;
+    if (a.zero_scalar && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.zero_scalar = 0.0;
 
     for (int i = i0; i < i1; ++i) {
         // fetch the row after next and the next intensity before touching this row
@@ -132,7 +143,7 @@ refract_kernel(const RefractArgs<T> a) {
             row[m] += f.ny;
         }
         float vnext = vin;
-        if (HAS_I && i + 1 < i1) { irow += f.ny; vnext = __ldg(irow); }
+        if (HAS_I && i + 1 < i1) { irow += f.ny; vnext = *irow; }
 
         const bool inner = inner_cols && i > 0 && i < f.nx - 1;   // warp-uniform
         float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
@@ -171,29 +182,58 @@ refract_kernel(const RefractArgs<T> a) {
         }
         float vo = ATT ? vin * expf(-arg) : vin;   // Sample.py:347
         float vr = vin;
-        clean(vo, dxo, dyo, a.clamp_x, a.clamp_y);
-        if (DUAL) clean(vr, dxr, dyr, a.clamp_x, a.clamp_y);
-        if (WRITE_D && live) {
-            const size_t pp = (size_t)(i + f.margin) * (f.ny + 2 * f.margin) + (j + f.margin);
-            a.dx_pad[pp] = dxo;
-            a.dy_pad[pp] = dyo;
+        if (live) {
+            const size_t p = (size_t)i * f.ny + j;
+            if (a.zero[0]) a.zero[0][p] = 0.f;
+            if (a.zero[1]) a.zero[1][p] = 0.f;
+            if (a.zero[2]) a.zero[2][p] = 0.f;
+            if (HAS_I && a.clear_input) const_cast<float*>(a.I_in)[p] = 0.f;
+        }
+        if (WRITE_D) {
+            clean(vo, dxo, dyo, a.clamp_x, a.clamp_y);
+            if (live) {
+                const size_t pp = (size_t)(i + f.margin) * (f.ny + 2 * f.margin) + (j + f.margin);
+                a.dx_pad[pp] = dxo;
+                a.dy_pad[pp] = dyo;
+            }
         }
         {
+            // A `simple` ray lands strictly inside the image, so |D| < N: the kill rule of
+            // refractionFileNumba2.py:61-64 cannot fire, and the |D| < 1e-12 -> 0 rule (:59-60) changes
+            // nothing at fp32 resolution.  Everything else is cleaned and takes the reference's edge rules.
             const FastRay q = fast_ray(i, j, vo, dxo, dyo, f.nx, f.ny);
             if (inner_cols && __all_sync(FULL_MASK, q.simple)) sp_obj.put_simple(q);
-            else sp_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
+            else {
+                if (!WRITE_D) clean(vo, dxo, dyo, a.clamp_x, a.clamp_y);
+                sp_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
+            }
         }
         if (DUAL) {
             const FastRay q = fast_ray(i, j, vr, dxr, dyr, f.nx, f.ny);
-            if (inner_cols && __all_sync(FULL_MASK, q.simple)) sp_ref.put_simple(q);
-            else sp_ref.put(live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray());
+            if (inner_cols && __all_sync(FULL_MASK, q.simple)) {
+                sp_ref.put_simple(q);
+                ref_sum += vr;
+            } else {
+                clean(vr, dxr, dyr, a.clamp_x, a.clamp_y);
+                const Ray qr = live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray();
+                sp_ref.put(qr);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ref_sum += ((qr.ok >> k) & 1u) ? qr.w[k] : 0.f;
+            }
         }
 #pragma unroll
         for (int m = 0; m < NM; ++m) { up[m] = mid[m]; mid[m] = dn[m]; dn[m] = nxt[m]; }
         vin = vnext;
     }
     sp_obj.finish();
-    if (DUAL) sp_ref.finish();
+    if (DUAL) {
+        sp_ref.finish();
+        if (a.sum_ref) {   // one double atomic per warp
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) ref_sum += __shfl_xor_sync(FULL_MASK, ref_sum, d);
+            if (lane == 0) atomicAdd(a.sum_ref, (double)ref_sum);
+        }
+    }
 }
 
 // Tuning knobs (paresis_set_tuning): deposit mode of the fused kernels, rows per warp.
@@ -305,6 +345,15 @@ extern "C" int paresis_refract_layers(const float* intensity_in, float intensity
                                       const paresis_layer* layers_host, int n_layers,
                                       float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
                                       int nx, int ny, int margin, int* flag, paresis_stream stream) {
+    return paresis_refract_layers_ex(intensity_in, intensity_uniform, layers_host, n_layers, out_obj, out_ref, dx_pad, dy_pad,
+                                     nx, ny, margin, flag, nullptr, stream);
+}
+
+extern "C" int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform,
+                                         const paresis_layer* layers_host, int n_layers,
+                                         float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
+                                         int nx, int ny, int margin, int* flag,
+                                         const paresis_refract_extras* extras, paresis_stream stream) {
     if (!layers_host || !out_obj || n_layers < 1 || n_layers > PARESIS_MAX_LAYERS) {
         set_last_error("paresis_refract_layers: need 1..%d layers and an output", PARESIS_MAX_LAYERS);
         return PARESIS_ERR_ARG;
@@ -335,6 +384,12 @@ extern "C" int paresis_refract_layers(const float* intensity_in, float intensity
     a.rows = pick_rows(nx, ny);
     a.flag = flag;
     cudaStream_t s = (cudaStream_t)stream;
+    if (extras) {
+        for (int k = 0; k < 3; ++k) a.zero[k] = extras->zero_fill[k];
+        a.clear_input = extras->clear_input != 0 && intensity_in != nullptr;
+        a.sum_ref = out_ref ? extras->sum_ref : nullptr;
+        a.zero_scalar = extras->zero_scalar;
+    }
     switch (n_layers) {
         case 1: return dispatch_layers<1>(a, s);
         case 2: return dispatch_layers<2>(a, s);

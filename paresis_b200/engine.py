@@ -20,6 +20,16 @@ from . import hostmath as hm
 IMAGES = ("sample", "reference", "propag", "white")
 
 
+class _PerPosition:
+    """Stands for "the membrane map of the position being computed" in a batched scene."""
+
+    def __repr__(self):
+        return "PER_POSITION"
+
+
+PER_POSITION = _PerPosition()
+
+
 class Layer:
     """One material of an object: a device thickness map (metres) or a uniform thickness."""
 
@@ -27,7 +37,7 @@ class Layer:
 
     def __init__(self, thickness, delta, beta):
         # delta / beta: {energy_keV: value}
-        if isinstance(thickness, torch.Tensor):
+        if isinstance(thickness, torch.Tensor) or thickness is PER_POSITION:
             self.map, self.uniform = thickness, None
         else:
             self.map, self.uniform = None, float(thickness)
@@ -88,7 +98,8 @@ class ImageFormation:
         self.seed = int(np.floor(time.time() * 100 % (2 ** 32 - 1))) if seed is None else int(seed)
         f32 = dict(device=self.device, dtype=torch.float32)
         n = (self.nx, self.ny)
-        self.i_bs = torch.empty(n, **f32)
+        self.i_bs = torch.zeros(n, **f32)      # invariant of paresis_rt_run: all zero between jobs
+        self._i_bs_dirty = False
         self.acc = {k: torch.zeros(n, **f32) for k in IMAGES}
         self.work = torch.empty(abi.detect_work_floats(self.nx, self.ny, self.os, self.det_x, self.det_y), **f32)
         self.expect = torch.empty((self.det_x, self.det_y), **f32)
@@ -145,13 +156,18 @@ class ImageFormation:
         out["_stack"] = stack
         return out
 
-    def _mean_energy(self, energies, bin_starts):
-        """Experiment.py:485-486, :523 from the running means of the reference accumulator."""
-        r = self.means[:len(energies)].cpu().numpy()
-        per = r.copy()
-        for i in range(1, len(per)):
-            if i not in bin_starts:
-                per[i] = r[i] - r[i - 1]
+    def _mean_energy(self, energies, bin_starts=None, sums=None):
+        """Experiment.py:485-486, :523.  ``sums`` = per-energy sums of the reference beam (ray tracing:
+        formed while it is deposited); otherwise ``self.means`` holds the running means of the
+        reference accumulator within each bin (Fresnel)."""
+        if sums is not None:
+            per = np.asarray(sums, dtype=np.float64) / float(self.nx * self.ny)
+        else:
+            r = self.means[:len(energies)].cpu().numpy()
+            per = r.copy()
+            for i in range(1, len(per)):
+                if i not in bin_starts:
+                    per[i] = r[i] - r[i - 1]
         return float(np.dot(per, energies)), float(per.sum())
 
     # ------------------------------------------------------------------ ray tracing
@@ -194,7 +210,9 @@ class ImageFormation:
             prop = [(t, d * g3, 0.0, 2 * k * b) for t, d, b in smp_maps]
             for dst, src in ((en.hop1, hop1), (en.hop2, hop2), (en.propag, prop)):
                 for m, (t, go, gr, at) in enumerate(src):
-                    dst[m].thickness, dst[m].grad_obj, dst[m].grad_ref, dst[m].atten = t.data_ptr(), go, gr, at
+                    # a NULL map = the membrane of the position at hand (paresis_rt_run_positions)
+                    dst[m].thickness = None if t is PER_POSITION else t.data_ptr()
+                    dst[m].grad_obj, dst[m].grad_ref, dst[m].atten = go, gr, at
                     keep.append(t)
             en.n_hop1, en.n_hop2, en.n_propag = len(hop1), len(hop2), len(prop)
             en.close_bin = 1 if ie in closing else 0
@@ -210,6 +228,7 @@ class ImageFormation:
         job.nx, job.ny, job.oversampling, job.det_x, job.det_y = self.nx, self.ny, self.os, self.det_x, self.det_y
         job.first_point, job.n_energies, job.energies_host = int(first), len(energies), energies
         job.i_bs = self.i_bs.data_ptr()
+        job.i_bs_dirty = 1 if self._i_bs_dirty else 0
         job.acc_sample, job.acc_ref = self.acc["sample"].data_ptr(), self.acc["reference"].data_ptr()
         job.acc_propag, job.acc_white = self.acc["propag"].data_ptr(), self.acc["white"].data_ptr()
         job.means, job.detect_work = self.means.data_ptr(), self.work.data_ptr()
@@ -248,12 +267,103 @@ class ImageFormation:
             job.out_propag, job.out_white = out["propag"].data_ptr(), out["white"].data_ptr()
         if wd:
             job.dx_pad, job.dy_pad = self.dx_pad.data_ptr(), self.dy_pad.data_ptr()
-        launches = n_e * (4 if first else 3) + len(closing) * (5 if first else 2)
-        abi.rt_run(job, launches, probe)
+        launches = n_e * (3 if first else 2) + len(closing) * (2 if first else 1)
+        self._run(job, launches, probe)
         if want_mean:
-            starts = {b[0] for b in bins}
-            out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], starts)
+            out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], sums=self.means[:n_e].cpu().numpy())
             self.check_flag()
+        return out
+
+    def _run(self, job, launches, probe=None):
+        """paresis_rt_run keeps I_bs all-zero between jobs; a failed call may leave it dirty."""
+        self._i_bs_dirty = True
+        abi.rt_run(job, launches, probe)
+        self._i_bs_dirty = False
+
+    # ------------------------------------------------------------------ many positions, one call
+    def _slots(self, n_slots, raster_bytes):
+        """Scratch sets of paresis_rt_run_positions: slot 0 is this engine's own buffers."""
+        f32 = dict(device=self.device, dtype=torch.float32)
+        cache = self.__dict__.setdefault("_slot_cache", [])
+        while len(cache) < n_slots:
+            k = len(cache)
+            cache.append(dict(
+                i_bs=self.i_bs if k == 0 else torch.zeros((self.nx, self.ny), **f32),
+                acc={name: (self.acc[name] if k == 0 else torch.empty((self.nx, self.ny), **f32)) for name in IMAGES},
+                work=None, stream=torch.cuda.Stream(device=self.device), dirty=False))
+        for c in cache[:n_slots]:
+            if c["work"] is None or c["work"].numel() < raster_bytes:
+                c["work"] = torch.empty(raster_bytes, device=self.device, dtype=torch.uint8)
+        return cache[:n_slots]
+
+    def compute_rt_positions(self, scene, plan, offsets, points, sequence_base=0, n_slots=2, probe_label=None,
+                             probe_events=None, want_means=True, buffers=None):
+        """``len(offsets)`` membrane positions in one library call (paresis_rt_run_positions): per
+        position the membrane is rasterised from ``plan`` (geometry.MembranePlan) at ``offsets[p]`` and
+        the whole per-energy pipeline runs, positions alternating between ``n_slots`` streams.
+
+        ``scene.membrane`` must hold one ``Layer(PER_POSITION, ...)`` for the rasterised map.
+        Returns a dict of device tensors: thickness [P, N, N], sample / reference [P, nbins, dx, dy],
+        propag / white [P0, nbins, dx, dy] for the positions with ``points[p] == 0`` (in order),
+        sums [P, n_energies] (float64 sums of the reference beam, see paresis_rt_job.means)."""
+        s = scene
+        n_pos = len(offsets)
+        bins = self.bins(s)
+        nbins, n_e = len(s.thresholds), len(s.spectrum)
+        closing = {b[-1] for b in bins[:nbins]}
+        energies, keep = self._rt_energies(s, list(range(n_e)), closing)
+        job, keep2 = self._rt_job(s, energies, False, 0)
+        firsts = [p for p in range(n_pos) if points[p] == 0]
+        f32 = dict(device=self.device, dtype=torch.float32)
+        if buffers is None:
+            buffers = dict(
+                thickness=torch.empty((n_pos, self.nx, self.ny), **f32),
+                images=torch.empty((n_pos, 2, nbins, self.det_x, self.det_y), **f32),
+                extra=torch.empty((max(len(firsts), 1), 2, nbins, self.det_x, self.det_y), **f32),
+                sums=torch.zeros((n_pos, n_e), device=self.device, dtype=torch.float64))
+        membrane = abi.Membrane(plan.table.data_ptr(), plan.table.shape[0], plan.pix, plan.layers, plan.margin)
+        raster_bytes = abi.lib.paresis_raster_work_bytes(plan.table.shape[0], plan.layers, self.nx, self.ny)
+        slots = self._slots(n_slots, raster_bytes)
+        c_slots = (abi.RtSlot * n_slots)()
+        for k, c in enumerate(slots):
+            sl = c_slots[k]
+            sl.i_bs = c["i_bs"].data_ptr()
+            sl.acc_sample, sl.acc_ref = c["acc"]["sample"].data_ptr(), c["acc"]["reference"].data_ptr()
+            sl.acc_propag, sl.acc_white = c["acc"]["propag"].data_ptr(), c["acc"]["white"].data_ptr()
+            sl.raster_work, sl.raster_work_bytes = c["work"].data_ptr(), c["work"].numel()
+            sl.stream = c["stream"].cuda_stream
+            sl.i_bs_dirty = 1 if (c["dirty"] or (k == 0 and self._i_bs_dirty)) else 0
+            c["dirty"] = True
+        self._i_bs_dirty = True
+        offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(n_pos, plan.layers, 2))
+        c_pos = (abi.RtPosition * n_pos)()
+        launches = 0
+        for p in range(n_pos):
+            cp = c_pos[p]
+            cp.offsets_host = offs[p].ctypes.data_as(abi.ctypes.POINTER(abi.ctypes.c_int64))
+            cp.thickness = buffers["thickness"][p].data_ptr()
+            cp.out_sample, cp.out_ref = buffers["images"][p, 0].data_ptr(), buffers["images"][p, 1].data_ptr()
+            first = points[p] == 0
+            if first:
+                k = firsts.index(p)
+                cp.out_propag, cp.out_white = buffers["extra"][k, 0].data_ptr(), buffers["extra"][k, 1].data_ptr()
+            cp.means = buffers["sums"][p].data_ptr() if want_means else None
+            cp.sequence = self.sequence(points[p], sequence_base)
+            cp.first_point = 1 if first else 0
+            if probe_events is not None:
+                e0, e1 = probe_events[p]
+                for e in (e0, e1):
+                    if not e.cuda_event:
+                        e.record()
+                cp.probe_start, cp.probe_end = e0.cuda_event, e1.cuda_event
+            launches += 2 + n_e * (3 if first else 2) + len(closing) * (2 if first else 1)
+        abi.rt_run_positions(job, membrane, c_pos, c_slots, launches, probe_label if probe_events is not None else None)
+        for c in slots:
+            c["dirty"] = False
+        self._i_bs_dirty = False
+        out = dict(thickness=buffers["thickness"], sample=buffers["images"][:, 0], reference=buffers["images"][:, 1],
+                   propag=buffers["extra"][:len(firsts), 0], white=buffers["extra"][:len(firsts), 1], sums=buffers["sums"],
+                   firsts=firsts, buffers=buffers)
         return out
 
     def accumulate_rt(self, scene, point_num, indices):
@@ -266,10 +376,8 @@ class ImageFormation:
         job, keep2 = self._rt_job(scene, energies, first, 0)
         dummy = torch.empty(1, device=self.device, dtype=torch.float32)
         job.out_sample = job.out_ref = job.out_propag = job.out_white = dummy.data_ptr()
-        abi.rt_run(job, len(indices) * (4 if first else 3))
-        running = self.means[:len(indices)].clone()
-        running[1:] -= self.means[:len(indices) - 1]
-        return running
+        self._run(job, len(indices) * (3 if first else 2))
+        return self.means[:len(indices)] / float(self.nx * self.ny)
 
     # ------------------------------------------------------------------ Fresnel
     def _reset(self, n_energies):
@@ -352,5 +460,5 @@ class ImageFormation:
                         a.zero_()
                     white_sum = 0.0
                     bin_starts.add(ie + 1)
-        out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts)
+        out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], bin_starts=bin_starts)
         return out

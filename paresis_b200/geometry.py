@@ -131,22 +131,35 @@ def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
     return _device_tables[dkey], ext_x, ext_y
 
 
-def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):
-    """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171).
+class MembranePlan:
+    """Everything about a segmented membrane that does not change from one position to the next
+    (getMembraneFromFile.py:84-124, :130-133): the device sphere table and the draw ranges."""
 
-    Two ``np.random.randint`` draws per layer, x first, from numpy's global stream (:139-140),
-    so ``np.random.seed`` reproduces the reference's membrane positions."""
-    dim_x, dim_y = int(dim_x), int(dim_y)
-    margin = int(np.ceil(10 * sample.myMeanSphereRadius / pix))
-    margin2 = int(np.floor(margin / 2))
-    table, ext_x, ext_y = _sphere_table(_MEMBRANE_FILE, sample.myMeanSphereRadius, dim_x, dim_y, pix)
-    offsets = []
-    for _ in range(sample.myNbOfLayers):
-        ox = np.random.randint(margin2, ext_x / pix - dim_x - margin2)
-        oy = np.random.randint(margin2, ext_y / pix - dim_y - margin2)
-        offsets.append((int(ox), int(oy)))
+    def __init__(self, sample, dim_x, dim_y, pix):
+        self.dim_x, self.dim_y, self.pix = int(dim_x), int(dim_y), float(pix)
+        self.layers = int(sample.myNbOfLayers)
+        self.margin = int(np.ceil(10 * sample.myMeanSphereRadius / pix))
+        self.margin2 = int(np.floor(self.margin / 2))
+        self.table, self.ext_x, self.ext_y = _sphere_table(_MEMBRANE_FILE, sample.myMeanSphereRadius, self.dim_x, self.dim_y, pix)
+
+    def draw_offsets(self):
+        """Two ``np.random.randint`` draws per layer, x first, from numpy's global stream (:139-140), so
+        ``np.random.seed`` reproduces the reference's membrane positions."""
+        offsets = []
+        for _ in range(self.layers):
+            ox = np.random.randint(self.margin2, self.ext_x / self.pix - self.dim_x - self.margin2)
+            oy = np.random.randint(self.margin2, self.ext_y / self.pix - self.dim_y - self.margin2)
+            offsets.append((int(ox), int(oy)))
+        return offsets
+
+
+def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):
+    """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171)."""
+    plan = MembranePlan(sample, dim_x, dim_y, pix)
+    offsets = plan.draw_offsets()
+    dim_x, dim_y = plan.dim_x, plan.dim_y
     grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)
-    abi.raster_spheres(table, pix, offsets, dim_x, dim_y, margin, grains)
+    abi.raster_spheres(plan.table, pix, offsets, dim_x, dim_y, plan.margin, grains)
     params = {'Average sphere radius': (sample.myMeanSphereRadius, 'um'),
               'Number of layers': (sample.myNbOfLayers, ''),
               'Support total thickness': (support_um, 'um')}

@@ -156,3 +156,45 @@ def test_main_script_writes_the_output_tree(shim, tmp_path):
     assert np.array_equal(img, np.round(img))            # Poisson counts
     reports = [f for f in os.listdir(os.path.dirname(os.path.dirname(root))) if f.endswith(".txt")]
     assert len(reports) == 1
+
+
+@pytest.mark.parametrize("name", ["Fil_Nylon_ID17", "B200_small_poly3"])
+def test_positions_in_one_call_match_one_by_one(shim, name):
+    """paresis_rt_run_positions (raster + pipeline of several positions, two in flight) gives the images
+    and the mean-energy sums of the position-by-position API; membrane offsets from the same seed."""
+    from paresis_b200 import geometry
+    d = dict(experimentName=name, filepath="unused/", overSampling=2, nbExpPoints=3, simulation_type="RayT",
+             expID="t", poissonNoise=False)
+    e = shim.Experiment(d)
+    mem = e.myMembrane
+    dims = e.exp_dict['studyDimensions']
+    np.random.seed(77)
+    single = []
+    for point in range(3):
+        mem.myGeometry = []
+        mem.getMyGeometry(dims, mem.membranePixelSize, 2, point, 3)
+        thick = np.array(mem.myGeometry[0])
+        e.exp_dict['meanEnergy'] = 0
+        res = e.computeSampleAndReferenceImages_RT(point)
+        single.append((thick, [np.array(r) for r in res[:4]], e.exp_dict['meanEnergy']))
+    thresholds = e.myDetector.det_param["myBinsThersholds"]
+    scene = e._scene(thresholds, per_position_membrane=True)
+    plan = geometry.MembranePlan(mem, dims[0], dims[1], mem.membranePixelSize)
+    np.random.seed(77)
+    offsets = [plan.draw_offsets() for _ in range(3)]
+    eng = e._get_engine()
+    for slots in (1, 2, 3):
+        out = eng.compute_rt_positions(scene, plan, offsets, [0, 1, 2], n_slots=slots)
+        torch.cuda.synchronize()
+        eng.check_flag()
+        energies = np.array([en for en, _ in scene.spectrum])
+        for p in range(3):
+            thick, imgs, mean_e = single[p]
+            assert rel_l2(out["thickness"][p].cpu().numpy(), thick) < 1e-6
+            assert rel_l2(out["sample"][p].cpu().numpy(), imgs[0]) < 1e-6
+            assert rel_l2(out["reference"][p].cpu().numpy(), imgs[1]) < 1e-6
+            sums = out["sums"][p].cpu().numpy()
+            assert abs(np.dot(sums, energies) / sums.sum() / mean_e - 1) < 1e-6
+        assert out["firsts"] == [0]
+        assert rel_l2(out["propag"][0].cpu().numpy(), single[0][1][2]) < 1e-6
+        assert rel_l2(out["white"][0].cpu().numpy(), single[0][1][3]) < 1e-6
