@@ -104,12 +104,16 @@ int paresis_refract_layers(const float* intensity_in, float intensity_uniform,
  *   clear_input   : intensity_in is zeroed once read (it is the scatter target of the next energy);
  *   zero_scalar   : *zero_scalar = 0 (the sum slot a later launch adds to);
  *   sum_ref       : *sum_ref += everything the reference beam deposits inside the image
- *                   (= nx*ny * np.mean(intensityReferenceBeforeDetection), Experiment.py:485-486). */
+ *                   (= nx*ny * np.mean(intensityReferenceBeforeDetection), Experiment.py:485-486);
+ *   intensity_scale: see below. */
 typedef struct {
     float* zero_fill[3];
     int clear_input;
     double* zero_scalar;
     double* sum_ref;
+    float intensity_scale;   /* > 0: the nominal beam intensity (e.g. I0 * flux).  Enables the shared-memory tile
+                                kernel, which accumulates in 32-bit fixed point with a unit of intensity_scale / 2^19;
+                                rays brighter than 2 x intensity_scale, or negative, still take the fp32 path. */
 } paresis_refract_extras;
 
 int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform,

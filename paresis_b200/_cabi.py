@@ -82,7 +82,7 @@ class Membrane(ctypes.Structure):
 
 class RefractExtras(ctypes.Structure):
     _fields_ = [("zero_fill", ctypes.c_void_p * 3), ("clear_input", ctypes.c_int), ("zero_scalar", ctypes.c_void_p),
-                ("sum_ref", ctypes.c_void_p)]
+                ("sum_ref", ctypes.c_void_p), ("intensity_scale", ctypes.c_float)]
 
 
 class C32(ctypes.Structure):
@@ -239,6 +239,14 @@ def set_tuning(key, value):
     _check(lib.paresis_set_tuning(int(key), int(value)), "paresis_set_tuning")
 
 
+if os.environ.get("PARESIS_TILE_CONFIG"):     # development knob: -1 = direct-to-L2 hop kernel, 0 / 1 = tile shapes
+    set_tuning(2, int(os.environ["PARESIS_TILE_CONFIG"]))
+
+
+if os.environ.get("PARESIS_ROWS"):            # development knob: source rows per warp of the hop kernels
+    set_tuning(1, int(os.environ["PARESIS_ROWS"]))
+
+
 def splat(intensity, dx, dy, out, margin=0, variant=2, flag=None):
     nx, ny = intensity.shape
     _check(lib.paresis_splat(_ptr(intensity, torch.float32), _ptr(dx, torch.float32), _ptr(dy, torch.float32),
@@ -258,7 +266,8 @@ def refract_phi(intensity, phi, out, distance, energy_kev, magnification, pixel_
 
 
 def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None,
-                   dx_pad=None, dy_pad=None, zero_fill=(), clear_input=False, zero_scalar=None, sum_ref=None):
+                   dx_pad=None, dy_pad=None, zero_fill=(), clear_input=False, zero_scalar=None, sum_ref=None,
+                   intensity_scale=0.0):
     """layers: list of (thickness tensor, grad_obj, grad_ref, atten); the keyword extras are
     paresis_refract_extras (zero_fill: up to 3 float32 images; zero_scalar / sum_ref: float64 scalars)."""
     n = len(layers)
@@ -276,6 +285,7 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
     extras.clear_input = 1 if clear_input else 0
     extras.zero_scalar = zero_scalar.data_ptr() if zero_scalar is not None else None
     extras.sum_ref = sum_ref.data_ptr() if sum_ref is not None else None
+    extras.intensity_scale = float(intensity_scale)
     _check(_timed(label, lambda: lib.paresis_refract_layers_ex(
         _ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n, _ptr(out_obj, torch.float32),
         _ptr(out_ref, torch.float32), _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,

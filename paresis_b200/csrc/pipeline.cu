@@ -50,6 +50,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
             fresh_bin = false;
         }
         x1.zero_scalar = job->means ? job->means + e : nullptr;
+        x1.intensity_scale = en.intensity_membrane;
         if (e == 0) probe(1, true);
         int rc = paresis_refract_layers_ex(nullptr, en.intensity_membrane, en.hop1, en.n_hop1, job->i_bs, nullptr, nullptr,
                                            nullptr, job->nx, job->ny, margin, job->flag, &x1, stream);
@@ -59,6 +60,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
         // cleared behind the pass; the reference beam is summed on the way (:485-486)
         paresis_refract_extras x2{};
         x2.clear_input = 1;
+        x2.intensity_scale = en.intensity_membrane;
         x2.sum_ref = job->means ? job->means + e : nullptr;
         if (e == 0) probe(2, true);
         rc = paresis_refract_layers_ex(job->i_bs, 0.f, en.hop2, en.n_hop2, job->acc_sample, job->acc_ref, nullptr, nullptr,

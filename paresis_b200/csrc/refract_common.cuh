@@ -1,0 +1,49 @@
+// Argument block and ray clean-up shared by the fused refraction kernels (refraction.cu, refract_tile.cu).
+#pragma once
+#include "splat.cuh"
+
+namespace paresis {
+
+template <typename T>
+struct RefractArgs {
+    const T* map[PARESIS_MAX_LAYERS];
+    float g_obj[PARESIS_MAX_LAYERS];
+    float g_ref[PARESIS_MAX_LAYERS];
+    float att[PARESIS_MAX_LAYERS];
+    const float* I_in;
+    float I_uniform;
+    float* out_obj;
+    float* out_ref;
+    float* dx_pad;   // optional: cleaned object-beam displacement, stored at (+margin, +margin)
+    float* dy_pad;
+    Frame f;
+    float clamp_x, clamp_y;   // rays with |D| above these are dropped (v2: nx, ny; v1: 1e3)
+    int rows;
+    int* flag;
+    // pipeline extras (all optional): buffers the NEXT kernel accumulates into are zero-filled here, pixel
+    // by pixel; the input intensity is cleared once read (so the next energy can scatter into it again);
+    // the sum of everything the reference beam deposits inside the image is added to *sum_ref
+    // (= N * mean of the reference image of this energy, Experiment.py:485-486).
+    float* zero[3];
+    bool clear_input;
+    double* sum_ref;
+    double* zero_scalar;
+    float intensity_scale;   // > 0: nominal beam intensity, enables the fixed-point tile kernel (refract_tile.cuh)
+};
+
+// refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
+__device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, float cy) {
+    if (fabsf(dx) < 1e-12f) dx = 0.f;
+    if (fabsf(dy) < 1e-12f) dy = 0.f;
+    const bool bx = fabsf(dx) > cx, by = fabsf(dy) > cy;
+    if (bx | by) v = 0.f;
+    if (bx) dx = 0.f;
+    if (by) dy = 0.f;
+}
+
+// Shared-memory tile variant (refract_tile.cu): config 0 = 16 rows / halo 4, 1 = 32 rows / halo 8.
+int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, int config, cudaStream_t s);
+// Two-columns-per-thread variant (refract_pair.cu); needs an even pitch and 8-byte aligned images.
+int dispatch_refract_pair(int n_layers, const RefractArgs<float>& a, int rows_override, cudaStream_t s);
+
+}  // namespace paresis

@@ -10,7 +10,7 @@
 // no tensor cores (there is no contraction on this path).
 #include <math.h>
 
-#include "splat.cuh"
+#include "refract_common.cuh"
 
 namespace paresis {
 
@@ -59,42 +59,6 @@ splat_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const fl
 // ---------------------------------------------------------------------------------------------
 // Fused: thickness (or phase) maps -> transmission -> gradient -> displacement -> scatter
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-struct RefractArgs {
-    const T* map[PARESIS_MAX_LAYERS];
-    float g_obj[PARESIS_MAX_LAYERS];
-    float g_ref[PARESIS_MAX_LAYERS];
-    float att[PARESIS_MAX_LAYERS];
-    const float* I_in;
-    float I_uniform;
-    float* out_obj;
-    float* out_ref;
-    float* dx_pad;   // optional: cleaned object-beam displacement, stored at (+margin, +margin)
-    float* dy_pad;
-    Frame f;
-    float clamp_x, clamp_y;   // rays with |D| above these are dropped (v2: nx, ny; v1: 1e3)
-    int rows;
-    int* flag;
-    // pipeline extras (all optional): buffers the NEXT kernel accumulates into are zero-filled here, pixel
-    // by pixel; the input intensity is cleared once read (so the next energy can scatter into it again);
-    // the sum of everything the reference beam deposits inside the image is added to *sum_ref
-    // (= N * mean of the reference image of this energy, Experiment.py:485-486).
-    float* zero[3];
-    bool clear_input;
-    double* sum_ref;
-    double* zero_scalar;
-};
-
-// refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
-__device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, float cy) {
-    if (fabsf(dx) < 1e-12f) dx = 0.f;
-    if (fabsf(dy) < 1e-12f) dy = 0.f;
-    const bool bx = fabsf(dx) > cx, by = fabsf(dy) > cy;
-    if (bx | by) v = 0.f;
-    if (bx) dx = 0.f;
-    if (by) dy = 0.f;
-}
-
 template <typename T, int NM, bool DUAL, bool HAS_I, bool ATT, bool WRITE_D, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 refract_kernel(const RefractArgs<T> a) {
@@ -239,6 +203,17 @@ refract_kernel(const RefractArgs<T> a) {
 // Tuning knobs (paresis_set_tuning): deposit mode of the fused kernels, rows per warp.
 static int g_fused_mode = 2;
 static int g_rows_override = 0;
+// which fused hop kernel runs: 0 / 1 = fixed-point shared-memory tiles with halo 4 / 8 (refract_tile.cu; production,
+// needs paresis_refract_extras.intensity_scale), 2 = two columns per thread straight to L2 (refract_pair.cu),
+// -1 = one column per thread straight to L2 (this file; the fallback for everything else)
+static int g_tile_config = 0;
+
+static bool pair_aligned(const RefractArgs<float>& a) {
+    uintptr_t bits = reinterpret_cast<uintptr_t>(a.out_obj) | reinterpret_cast<uintptr_t>(a.out_ref) | reinterpret_cast<uintptr_t>(a.I_in);
+    for (int m = 0; m < PARESIS_MAX_LAYERS; ++m) bits |= reinterpret_cast<uintptr_t>(a.map[m]);
+    for (int k = 0; k < 3; ++k) bits |= reinterpret_cast<uintptr_t>(a.zero[k]);
+    return (bits & 7) == 0;
+}
 
 // rows per warp: enough blocks for ~2 waves of 148 SMs x 8 resident blocks, few halo re-reads
 static int pick_rows(int nx, int ny) {
@@ -273,6 +248,8 @@ template <int NM>
 static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
     const bool dual = a.out_ref != nullptr, has_i = a.I_in != nullptr;
     const bool wd = a.dx_pad != nullptr;
+    if (!wd && g_tile_config == 2 && (a.f.ny & 1) == 0 && pair_aligned(a)) return dispatch_refract_pair(NM, a, g_rows_override, s);
+    if (!wd && (g_tile_config == 0 || g_tile_config == 1) && a.intensity_scale > 0.f) return dispatch_refract_tile(NM, a, g_tile_config, s);
     if (dual) return has_i ? launch_refract<float, NM, true, true, true>(a, false, s)
                            : launch_refract<float, NM, true, false, true>(a, false, s);
     return has_i ? launch_refract<float, NM, false, true, true>(a, wd, s)
@@ -287,6 +264,7 @@ extern "C" int paresis_set_tuning(int key, int value) {
     switch (key) {
         case 0: g_fused_mode = value == 0 ? 0 : 2; return PARESIS_OK;
         case 1: g_rows_override = value; return PARESIS_OK;
+        case 2: g_tile_config = value < 0 ? -1 : (value > 2 ? 2 : value); return PARESIS_OK;
         default: set_last_error("paresis_set_tuning: unknown key %d", key); return PARESIS_ERR_ARG;
     }
 }
@@ -389,6 +367,7 @@ extern "C" int paresis_refract_layers_ex(const float* intensity_in, float intens
         a.clear_input = extras->clear_input != 0 && intensity_in != nullptr;
         a.sum_ref = out_ref ? extras->sum_ref : nullptr;
         a.zero_scalar = extras->zero_scalar;
+        a.intensity_scale = extras->intensity_scale > 0.f && extras->intensity_scale < 3.0e38f ? extras->intensity_scale : 0.f;
     }
     switch (n_layers) {
         case 1: return dispatch_layers<1>(a, s);
