@@ -198,6 +198,8 @@ typedef struct {
 
 typedef struct {
     const double* spheres; int n_spheres; double pix_um; int n_layers; int margin;   /* see paresis_raster_spheres */
+    const float* field; int field_x, field_y;   /* optional sphere field (paresis_raster_field): positions are then
+                                                   cut from it (paresis_membrane_from_field) instead of rasterised */
 } paresis_membrane;
 
 int paresis_rt_run_positions(const paresis_rt_job* job_host, const paresis_membrane* membrane_host,
@@ -295,6 +297,23 @@ int paresis_raster_spheres(const double* spheres, int n_spheres, double pix_um,
                            const int64_t* offsets_host, int n_layers, int dim_x, int dim_y,
                            int margin, float* thickness_out, void* work, size_t work_bytes,
                            paresis_stream stream);
+
+/* The same membrane without re-rasterising it at every position.  getMembraneFromFile.py:139-161 moves
+ * the sphere list by INTEGER pixel offsets per layer, so the grain map of a position is a sum of shifted
+ * windows of one "sphere field": the caps of the whole (tiled) list on its own canvas.
+ *   paresis_raster_field        : field[field_x][field_y] = that canvas, metres (= paresis_raster_spheres with
+ *                                 one layer, zero offsets, zero margin); once per experiment.
+ *   paresis_membrane_from_field : thickness_out[r][c] = sum_l field[ox_l + margin + r][oy_l + margin + c]
+ *                                 (0 outside the field); once per position.
+ * Identical to paresis_raster_spheres up to fp32 summation order PROVIDED no grain reaches further than
+ * margin/2 pixels (floor(r/pix) + 1 <= margin/2): the reference only accepts grains whose centre lies within
+ * margin/2 of the field of view (:151), which then never clips a grain that touches it.  The caller checks
+ * that (paresis_b200/geometry.py does) and uses paresis_raster_spheres otherwise. */
+int paresis_raster_field(const double* spheres, int n_spheres, double pix_um, int field_x, int field_y,
+                         float* field, void* work, size_t work_bytes, paresis_stream stream);
+int paresis_membrane_from_field(const float* field, int field_x, int field_y, const int64_t* offsets_host,
+                                int n_layers, int margin, int dim_x, int dim_y, float* thickness_out,
+                                paresis_stream stream);
 
 /* CreateSampleSphere -- Samples/createSampGeom.py:41-53. */
 int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, float* out,

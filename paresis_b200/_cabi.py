@@ -26,7 +26,7 @@ EXPORTS = (
     "paresis_detect_counts", "paresis_detect_counts_multi",
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
-    "paresis_refract_layers_ex",
+    "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
 )
 
 
@@ -77,7 +77,8 @@ class RtSlot(ctypes.Structure):
 
 class Membrane(ctypes.Structure):
     _fields_ = [("spheres", ctypes.c_void_p), ("n_spheres", ctypes.c_int), ("pix_um", ctypes.c_double),
-                ("n_layers", ctypes.c_int), ("margin", ctypes.c_int)]
+                ("n_layers", ctypes.c_int), ("margin", ctypes.c_int), ("field", ctypes.c_void_p),
+                ("field_x", ctypes.c_int), ("field_y", ctypes.c_int)]
 
 
 class RefractExtras(ctypes.Structure):
@@ -118,6 +119,8 @@ def _load():
         "paresis_poisson": [vp, vp, sz, u64, u64, vp],
         "paresis_bin_sum": [vp, ci, ci, ci, ci, vp, vp],
         "paresis_raster_spheres": [vp, ci, cd, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp, sz, vp],
+        "paresis_raster_field": [vp, ci, cd, ci, ci, vp, vp, sz, vp],
+        "paresis_membrane_from_field": [vp, ci, ci, ctypes.POINTER(ctypes.c_int64), ci, ci, ci, ci, vp, vp],
         "paresis_sphere_map": [cd, ci, ci, cd, vp, vp],
         "paresis_cylinder_map": [cd, cd, ci, ci, cd, vp, vp],
         "paresis_fill": [vp, cf, sz, vp],
@@ -421,6 +424,27 @@ def raster_spheres(spheres, pix_um, offsets, dim_x, dim_y, margin, out):
         offs.shape[0], dim_x, dim_y, margin, _ptr(out, torch.float32), ctypes.c_void_p(work.data_ptr()), work.numel(),
         _stream())), "paresis_raster_spheres")
     _count(2)
+
+
+def raster_field(spheres, pix_um, field):
+    """paresis_raster_field: the caps of the whole sphere list on its own canvas (once per experiment)."""
+    fx, fy = field.shape
+    need = lib.paresis_raster_work_bytes(spheres.shape[0], 1, fx, fy)
+    work = torch.empty(need, device=field.device, dtype=torch.uint8)
+    _check(lib.paresis_raster_field(_ptr(spheres, torch.float64), spheres.shape[0], float(pix_um), fx, fy,
+                                    _ptr(field, torch.float32), ctypes.c_void_p(work.data_ptr()), work.numel(), _stream()),
+           "paresis_raster_field")
+    _count(2)
+    torch.cuda.current_stream().synchronize()      # `work` is released when this returns
+
+
+def membrane_from_field(field, offsets, margin, dim_x, dim_y, out):
+    offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(-1, 2))
+    fx, fy = field.shape
+    _check(_timed("raster_spheres", lambda: lib.paresis_membrane_from_field(
+        _ptr(field, torch.float32), fx, fy, offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), offs.shape[0], margin,
+        dim_x, dim_y, _ptr(out, torch.float32), _stream())), "paresis_membrane_from_field")
+    _count()
 
 
 def sphere_map(radius_um, dim_x, dim_y, pix_um, out):

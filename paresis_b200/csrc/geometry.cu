@@ -132,6 +132,35 @@ raster_gather_kernel(const int* __restrict__ n_caps_all, const Cap* __restrict__
     }
 }
 
+// One membrane position from the once-rasterised sphere field: the grain map is translation
+// invariant (getMembraneFromFile.py:139-161 only shifts the list by integer pixels per layer), so
+// out[r][c] = sum over layers of field[ox_l + margin + r][oy_l + margin + c].
+// A thread owns four consecutive columns; window starts are arbitrary, so loads are scalar (coalesced).
+__global__ void __launch_bounds__(256)
+membrane_from_field_kernel(const float* __restrict__ field, int field_x, int field_y, LayerOffsets off, int n_layers, int margin,
+                           int dim_x, int dim_y, float* __restrict__ out) {
+    const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int r = blockIdx.y;
+    if (c >= dim_y) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < n_layers; ++l) {
+        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c;
+        if (fr < 0 || fr >= field_x) continue;
+        const float* src = field + (size_t)fr * field_y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (fc + k >= 0 && fc + k < field_y) acc[k] += __ldg(src + fc + k);
+    }
+    float* o = out + (size_t)r * dim_y + c;
+    if (c + 3 < dim_y && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c + k < dim_y) o[k] = acc[k];
+    }
+}
+
 __global__ void sphere_map_kernel(double rad, double scale_m, int dim_x, int dim_y, float* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
@@ -221,6 +250,31 @@ extern "C" int paresis_raster_spheres(const double* spheres, int n_spheres, doub
                                                                             2.0f * (float)(pix_um * 1e-6), tiles_y, count, entries,
                                                                             thickness_out);
     PARESIS_LAUNCH_CHECK("raster_gather_kernel");
+    return PARESIS_OK;
+}
+
+extern "C" int paresis_raster_field(const double* spheres, int n_spheres, double pix_um, int field_x, int field_y,
+                                    float* field, void* work, size_t work_bytes, paresis_stream stream) {
+    const int64_t zero[2] = {0, 0};
+    return paresis_raster_spheres(spheres, n_spheres, pix_um, zero, 1, field_x, field_y, 0, field, work, work_bytes, stream);
+}
+
+extern "C" int paresis_membrane_from_field(const float* field, int field_x, int field_y, const int64_t* offsets_host,
+                                           int n_layers, int margin, int dim_x, int dim_y, float* thickness_out,
+                                           paresis_stream stream) {
+    if (!field || !offsets_host || !thickness_out || field_x < 1 || field_y < 1 || n_layers < 1 || n_layers > MAX_MEMBRANE_LAYERS ||
+        margin < 0 || dim_x < 1 || dim_y < 1) {
+        set_last_error("paresis_membrane_from_field: bad arguments (layers 1..%d)", MAX_MEMBRANE_LAYERS);
+        return PARESIS_ERR_ARG;
+    }
+    LayerOffsets off{};
+    for (int l = 0; l < n_layers; ++l) {
+        off.x[l] = offsets_host[2 * l];
+        off.y[l] = offsets_host[2 * l + 1];
+    }
+    membrane_from_field_kernel<<<dim3(div_up(dim_y, 1024), dim_x), 256, 0, (cudaStream_t)stream>>>(
+        field, field_x, field_y, off, n_layers, margin, dim_x, dim_y, thickness_out);
+    PARESIS_LAUNCH_CHECK("membrane_from_field_kernel");
     return PARESIS_OK;
 }
 

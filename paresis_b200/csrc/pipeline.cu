@@ -149,8 +149,12 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
         }
         const bool probe_raster = job->probe == 4 && pos.probe_start && pos.probe_end;
         if (probe_raster) cudaEventRecord((cudaEvent_t)pos.probe_start, (cudaStream_t)slot.stream);
-        rc = paresis_raster_spheres(mem->spheres, mem->n_spheres, mem->pix_um, pos.offsets_host, mem->n_layers, job->nx,
-                                    job->ny, mem->margin, pos.thickness, slot.raster_work, slot.raster_work_bytes, slot.stream);
+        if (mem->field)
+            rc = paresis_membrane_from_field(mem->field, mem->field_x, mem->field_y, pos.offsets_host, mem->n_layers, mem->margin,
+                                             job->nx, job->ny, pos.thickness, slot.stream);
+        else
+            rc = paresis_raster_spheres(mem->spheres, mem->n_spheres, mem->pix_um, pos.offsets_host, mem->n_layers, job->nx,
+                                        job->ny, mem->margin, pos.thickness, slot.raster_work, slot.raster_work_bytes, slot.stream);
         if (probe_raster) cudaEventRecord((cudaEvent_t)pos.probe_end, (cudaStream_t)slot.stream);
         if (rc) return rc;
         // a NULL layer map stands for this position's membrane

@@ -321,7 +321,10 @@ class ImageFormation:
                 images=torch.empty((n_pos, 2, nbins, self.det_x, self.det_y), **f32),
                 extra=torch.empty((max(len(firsts), 1), 2, nbins, self.det_x, self.det_y), **f32),
                 sums=torch.zeros((n_pos, n_e), device=self.device, dtype=torch.float64))
-        membrane = abi.Membrane(plan.table.data_ptr(), plan.table.shape[0], plan.pix, plan.layers, plan.margin)
+        field = plan.field()
+        membrane = abi.Membrane(plan.table.data_ptr(), plan.table.shape[0], plan.pix, plan.layers, plan.margin,
+                                field.data_ptr() if field is not None else None,
+                                field.shape[0] if field is not None else 0, field.shape[1] if field is not None else 0)
         raster_bytes = abi.lib.paresis_raster_work_bytes(plan.table.shape[0], plan.layers, self.nx, self.ny)
         slots = self._slots(n_slots, raster_bytes)
         c_slots = (abi.RtSlot * n_slots)()
@@ -356,7 +359,7 @@ class ImageFormation:
                     if not e.cuda_event:
                         e.record()
                 cp.probe_start, cp.probe_end = e0.cuda_event, e1.cuda_event
-            launches += 2 + n_e * (3 if first else 2) + len(closing) * (2 if first else 1)
+            launches += (1 if field is not None else 2) + n_e * (3 if first else 2) + len(closing) * (2 if first else 1)
         abi.rt_run_positions(job, membrane, c_pos, c_slots, launches, probe_label if probe_events is not None else None)
         for c in slots:
             c["dirty"] = False

@@ -83,11 +83,14 @@ def from_host(array):
 _MEMBRANE_FILE = "Samples/Membranes/CuSn.txt"
 _host_tables = {}     # parsed + rescaled + tiled sphere lists, keyed by file identity and geometry
 _device_tables = {}   # their device copies
+_device_fields = {}   # sphere fields rasterised from them (paresis_raster_field)
+FIELD_BYTES_LIMIT = 16 << 30   # beyond this the membrane is rasterised per position instead
 
 
 def drop_device_tables():
     """Forget the device copies (the next position uploads the sphere list again)."""
     _device_tables.clear()
+    _device_fields.clear()
 
 
 def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
@@ -123,6 +126,7 @@ def _sphere_table(path, mean_radius, dim_x, dim_y, pix):
             ext_y += step
         _host_tables.clear()
         _device_tables.clear()
+        _device_fields.clear()
         _host_tables[key] = (np.ascontiguousarray(tab), ext_x, ext_y)
     tab, ext_x, ext_y = _host_tables[key]
     dkey = key + (torch.cuda.current_device(),)
@@ -141,6 +145,23 @@ class MembranePlan:
         self.margin = int(np.ceil(10 * sample.myMeanSphereRadius / pix))
         self.margin2 = int(np.floor(self.margin / 2))
         self.table, self.ext_x, self.ext_y = _sphere_table(_MEMBRANE_FILE, sample.myMeanSphereRadius, self.dim_x, self.dim_y, pix)
+        self._field_key = (self.table.data_ptr(), self.pix, self.margin, torch.cuda.current_device())
+
+    def field(self):
+        """The sphere field of this membrane (device tensor), or None when positions must be rasterised one by
+        one: a grain reaching further than margin/2 pixels would be clipped by the reference's acceptance window
+        (getMembraneFromFile.py:151), which a shifted window of the field cannot reproduce."""
+        if self._field_key not in _device_fields:
+            fx = int(np.ceil(self.ext_x / self.pix)) + self.margin + 1
+            fy = int(np.ceil(self.ext_y / self.pix)) + self.margin + 1
+            reach = int(np.floor(float(self.table[:, 2].max().item()) / self.pix)) + 1 if self.table.shape[0] else 0
+            if reach > self.margin2 or fx * fy * 4 > FIELD_BYTES_LIMIT:
+                _device_fields[self._field_key] = None
+            else:
+                field = torch.empty((fx, fy), device=self.table.device, dtype=torch.float32)
+                abi.raster_field(self.table, self.pix, field)
+                _device_fields[self._field_key] = field
+        return _device_fields[self._field_key]
 
     def draw_offsets(self):
         """Two ``np.random.randint`` draws per layer, x first, from numpy's global stream (:139-140), so
@@ -159,7 +180,11 @@ def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=Non
     offsets = plan.draw_offsets()
     dim_x, dim_y = plan.dim_x, plan.dim_y
     grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)
-    abi.raster_spheres(plan.table, pix, offsets, dim_x, dim_y, plan.margin, grains)
+    field = plan.field()
+    if field is not None:
+        abi.membrane_from_field(field, offsets, plan.margin, dim_x, dim_y, grains)
+    else:
+        abi.raster_spheres(plan.table, pix, offsets, dim_x, dim_y, plan.margin, grains)
     params = {'Average sphere radius': (sample.myMeanSphereRadius, 'um'),
               'Number of layers': (sample.myNbOfLayers, ''),
               'Support total thickness': (support_um, 'um')}
