@@ -33,62 +33,60 @@ __device__ __forceinline__ void red_add4(float* p, const float4& v) {
 }
 
 // r, c of the lower cell and the four weights; `simple` = all four cells strictly inside the image
-struct TileRay {
-    int r, c;
-    float v, fx, fy;          // intensity and the fractional displacement (weights (1-f, f) per axis)
-    bool simple;
-};
-
 constexpr int FIX_BITS = 19;  // with 16 x 256 rays per tile: rays up to 2 x intensity_scale stay in fixed point
 
-__device__ __forceinline__ TileRay tile_ray(int i, int j, float v, float dx, float dy, int nx, int ny) {
-    TileRay q;
-    const float flx = floorf(dx), fly = floorf(dy);
-    q.fx = dx - flx; q.fy = dy - fly;
-    q.v = v;
-    q.r = i + __float2int_rd(dx);    // saturating; wrap-around fails `simple`
-    q.c = j + __float2int_rd(dy);
-    q.simple = ((unsigned)q.r < (unsigned)(nx - 1)) & ((unsigned)q.c < (unsigned)(ny - 1));
-    return q;
-}
+__device__ __forceinline__ float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-template <int SR, int SC>
-struct TileSplatter {
-    unsigned* tile;  // [SR][SC] shared, fixed point
-    float* out;      // global image
-    int rlo, clo, ny;
-    float scale, vmax;   // fixed units per intensity unit; rays at or above vmax bypass the tile
-    bool bad;
-
-    __device__ __forceinline__ void init(unsigned* tile_, float* out_, int rlo_, int clo_, int ny_, float scale_, float vmax_) {
-        tile = tile_; out = out_; rlo = rlo_; clo = clo_; ny = ny_; scale = scale_; vmax = vmax_; bad = false;
-    }
-    // all four cells inside the image (q.simple): tile if it reaches, else straight to L2
-    __device__ __forceinline__ void put(const TileRay& q) {
-        bad |= !(fabsf(fmaf(q.fx + q.fy, 0.f, q.v)) <= 3.0e38f);   // NaN / Inf in the intensity or the displacement
-        const unsigned sr = (unsigned)(q.r - rlo), sc = (unsigned)(q.c - clo);
-        if (sr < (unsigned)(SR - 1) && sc < (unsigned)(SC - 1) && q.v >= 0.f && q.v < vmax) {
-            // exact split of V between the four cells: 24-bit fractions, V < 2^24
-            const unsigned V = __float2uint_rn(q.v * scale);
-            const unsigned fxi = __float2uint_rn(q.fx * 16777216.f), fyi = __float2uint_rn(q.fy * 16777216.f);
-            const unsigned V1 = __umulhi(V << 8, fxi), V0 = V - V1;
-            const unsigned W1 = __umulhi(V0 << 8, fyi), W3 = __umulhi(V1 << 8, fyi);
-            unsigned* t = tile + sr * SC + sc;
-            atomicAdd(t, V0 - W1);
-            atomicAdd(t + 1, W1);
-            atomicAdd(t + SC, V1 - W3);
-            atomicAdd(t + SC + 1, W3);
-        } else {
-            const float v1 = q.v * q.fx, v0 = q.v - v1;
-            const float w1 = v0 * q.fy, w0 = v0 - w1, w3 = v1 * q.fy, w2 = v1 - w3;
-            float* p = out + (size_t)q.r * ny + q.c;
-            if (w0 != 0.f) red_add(p, w0);
-            if (w1 != 0.f) red_add(p + 1, w1);
-            if (w2 != 0.f) red_add(p + ny, w2);
-            if (w3 != 0.f) red_add(p + ny + 1, w3);
-        }
-    }
+// Block-uniform description of one output image: shared tile, global image, and the window of lower cells
+// (r, c) whose four cells lie both inside the tile and strictly inside the image.
+struct TileTarget {
+    unsigned* tile;
+    float* out;
+    int r0, c0;            // first lower cell of the window (image coordinates)
+    unsigned nr, nc;       // window extent: lower cells r0 .. r0+nr-1, c0 .. c0+nc-1
+    int rlo, clo;          // image coordinates of tile cell (0, 0)
 };
+
+// One ray.  Fast path: fixed-point deposit into the tile (native ATOMS.ADD).  Everything else -- the ray leaves
+// the tile, touches the image border, is too bright / negative / not finite -- goes to L2 in fp32, cell by cell;
+// cells outside the image are dropped, which is what zero-padding, scattering and cropping does
+// (refractionFileNumba2.py:65-78; the |D| > N kill of :61-64 only removes rays that land outside anyway).
+// Returns what was deposited inside the image.
+template <int SC>
+__device__ __forceinline__ float deposit(const TileTarget& t, int i, int j, float v, float dx, float dy, int nx, int ny,
+                                         float scale, unsigned vmax_bits, bool live, bool& bad) {
+    const float flx = floorf(dx), fly = floorf(dy);
+    const float fx = dx - flx, fy = dy - fly;
+    const int r = i + __float2int_rd(dx), c = j + __float2int_rd(dy);   // saturating
+    // v in [0, vmax) as one unsigned compare on the bit pattern (negative and NaN patterns are larger)
+    const bool fast = live && (unsigned)(r - t.r0) < t.nr && (unsigned)(c - t.c0) < t.nc && __float_as_uint(v) < vmax_bits &&
+                      fx + fy < 3.f;
+    if (fast) {
+        const float vs = v * scale;
+        const float v1 = vs * fx, v0 = vs - v1;
+        const float w1 = v0 * fy, w0 = v0 - w1, w3 = v1 * fy, w2 = v1 - w3;
+        unsigned* p = t.tile + (r - t.rlo) * SC + (c - t.clo);
+        atomicAdd(p, __float2uint_rn(w0));
+        atomicAdd(p + 1, __float2uint_rn(w1));
+        atomicAdd(p + SC, __float2uint_rn(w2));
+        atomicAdd(p + SC + 1, __float2uint_rn(w3));
+        return v;
+    }
+    float sum = 0.f;
+    if (live) {
+        const float v1 = v * fx, v0 = v - v1;
+        const float w1 = v0 * fy, w0 = v0 - w1, w3 = v1 * fy, w2 = v1 - w3;
+        bad |= !(fabsf(w0 + w3) <= 3.0e38f);
+        const bool ra = (unsigned)r < (unsigned)nx, rb = (unsigned)(r + 1) < (unsigned)nx;
+        const bool ca = (unsigned)c < (unsigned)ny, cb = (unsigned)(c + 1) < (unsigned)ny;
+        float* p = t.out + (long long)r * ny + c;
+        if (ra && ca && w0 != 0.f) { red_add(p, w0); sum += w0; }
+        if (ra && cb && w1 != 0.f) { red_add(p + 1, w1); sum += w1; }
+        if (rb && ca && w2 != 0.f) { red_add(p + ny, w2); sum += w2; }
+        if (rb && cb && w3 != 0.f) { red_add(p + ny + 1, w3); sum += w3; }
+    }
+    return sum;
+}
 
 // Tile -> image: dense 128-bit REDs, all-zero quads skipped; image borders and odd pitches fall back to scalars.
 template <int SR, int SC>
@@ -119,20 +117,25 @@ __global__ void __launch_bounds__(TILE_COLS)
 refract_tile_kernel(const RefractArgs<float> a) {
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     static_assert(H % 4 == 0 && H >= 4, "halo must keep the tile 16-byte aligned");
-    static_assert((long)TR * TILE_COLS << FIX_BITS <= (1L << 32), "a tile of the brightest rays must fit in 32 bits");
+    static_assert(((1ull << 32) / (TR * TILE_COLS)) >= (2ull << FIX_BITS), "rays up to 2 x intensity_scale must fit the fixed-point tile");
     extern __shared__ __align__(16) unsigned tile_smem[];
-    unsigned* tobj = tile_smem;
-    unsigned* tref = tile_smem + SR * SC;
 
     const Frame f = a.f;
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * TILE_COLS + threadIdx.x;
-    const int i0 = blockIdx.y * TR;
-    const int i1 = min(i0 + TR, f.nx);
-    const int rlo = i0 - H, clo = blockIdx.x * TILE_COLS - H;
+    const int i0 = blockIdx.y * a.rows;          // a.rows <= TR: picked on the host to fill whole waves
+    const int i1 = min(i0 + a.rows, f.nx);
     const bool live = j < f.ny;
     const int jc = live ? j : f.ny - 1;  // dead lanes read a valid address, contribute nothing
     const bool inner_cols = __all_sync(FULL_MASK, live && j > 0 && j < f.ny - 1);
+
+    TileTarget tobj, tref;
+    tobj.tile = tile_smem; tobj.out = a.out_obj;
+    tobj.rlo = i0 - H; tobj.clo = blockIdx.x * TILE_COLS - H;
+    tobj.r0 = max(tobj.rlo, 0); tobj.c0 = max(tobj.clo, 0);
+    tobj.nr = (unsigned)max(min(tobj.rlo + SR - 1, f.nx - 1) - tobj.r0, 0);
+    tobj.nc = (unsigned)max(min(tobj.clo + SC - 1, f.ny - 1) - tobj.c0, 0);
+    tref = tobj; tref.tile = tile_smem + SR * SC; tref.out = a.out_ref;
 
     {   // zero the tile(s)
         uint4* z = reinterpret_cast<uint4*>(tile_smem);
@@ -140,123 +143,100 @@ refract_tile_kernel(const RefractArgs<float> a) {
         for (int k = threadIdx.x; k < NZ; k += TILE_COLS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // rolling rows: up = i-1, mid = i, dn = i+1, n1 = i+2 (in flight from the previous step); row i+3 is fetched now
-    float up[NM], mid[NM], dn[NM], n1[NM];
+    // Row ring: slot k of step s holds row i-1+k; rows i-1, i, i+1 are used, row i+2 is in flight and row i+3 is
+    // fetched now.  The loop is unrolled by the ring size so that the rotation is register renaming -- a rotation by
+    // moves would wait for the load issued in the same step.  `hal` = the column next to the strip (edge lanes),
+    // `inten` = the input intensity, same indexing.
+    constexpr int RING = 5;
+    float row[RING][NM], hal[RING][NM], inten[RING];
     const bool edge_lane = lane == 0 || lane == 31;
     const int jh = min(max(lane == 0 ? jc - 1 : jc + 1, 0), f.ny - 1);
     int off = i0 * f.ny + jc;          // element offset of (i, jc); nx*ny < 2^30 (host check)
     int offh = i0 * f.ny + jh;         // (i, column next to the strip) for the edge lanes
+    const int last = (f.nx - 1) * f.ny;   // offsets are clamped to the image instead of predicating the loads
 #pragma unroll
-    for (int m = 0; m < NM; ++m) {
-        const float* t = a.map[m];
-        mid[m] = __ldg(t + off);
-        up[m] = i0 > 0 ? __ldg(t + off - f.ny) : mid[m];
-        dn[m] = i0 + 1 < f.nx ? __ldg(t + off + f.ny) : mid[m];
-        n1[m] = i0 + 2 < f.nx ? __ldg(t + off + 2 * f.ny) : dn[m];
+    for (int k = 0; k < RING - 1; ++k) {
+        const int d = (k - 1) * f.ny;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            row[k][m] = __ldg(a.map[m] + min(max(off + d, jc), last + jc));
+            hal[k][m] = edge_lane ? __ldg(a.map[m] + min(max(offh + d, jh), last + jh)) : 0.f;
+        }
+        // plain loads: with clear_input the same thread stores to this address after reading it
+        inten[k] = HAS_I ? a.I_in[min(max(off + d, jc), last + jc)] : a.I_uniform;
     }
-    // plain loads: with clear_input the same thread stores to this address after reading it
-    float vin = HAS_I ? a.I_in[off] : a.I_uniform;
-    float vn1 = (HAS_I && i0 + 1 < i1) ? a.I_in[off + f.ny] : vin;
 
-    TileSplatter<SR, SC> sp_obj, sp_ref;
-    // rays below vmax convert to V < 2^32 / (TR * 256): the whole tile cannot overflow one cell
+    // rays below vmax convert to less than 2^32 / (TR * 256) - 4 units: a whole tile cannot overflow one cell
     const float fix_scale = (float)(1u << FIX_BITS) / a.intensity_scale;
-    const float fix_vmax = a.intensity_scale * (float)((1ull << 32) / ((unsigned long long)TR * TILE_COLS) - 2) / (float)(1u << FIX_BITS);
-    sp_obj.init(tobj, a.out_obj, rlo, clo, f.ny, fix_scale, fix_vmax);
-    if (DUAL) sp_ref.init(tref, a.out_ref, rlo, clo, f.ny, fix_scale, fix_vmax);
-    Splatter<0> slow_obj, slow_ref;    // reference edge rules, straight to L2
-    slow_obj.init(a.out_obj, f.ny, nullptr);
-    if (DUAL) slow_ref.init(a.out_ref, f.ny, nullptr);
+    const unsigned vmax_bits = __float_as_uint(a.intensity_scale * (float)((unsigned)((1ull << 32) / (TR * TILE_COLS)) - 8u) / (float)(1u << FIX_BITS));
+    const float neg_log2e = -1.4426950408889634f;
+    const bool zero_fill = a.zero[0] != nullptr;    // the host fills unused slots with a used pointer
+    const bool clear_in = HAS_I && a.clear_input;
+    bool bad = false;
     float ref_sum = 0.f;
     if (a.zero_scalar && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.zero_scalar = 0.0;
     __syncthreads();
 
-    for (int i = i0; i < i1; ++i) {
-        float n2[NM];
+    for (int ib = i0; ib < i1; ib += RING) {
 #pragma unroll
-        for (int m = 0; m < NM; ++m) n2[m] = (i + 3 < f.nx && i + 3 <= i1) ? __ldg(a.map[m] + off + 3 * f.ny) : n1[m];
-        float vn2 = vn1;
-        if (HAS_I && i + 2 < i1) vn2 = a.I_in[off + 2 * f.ny];
-
-        const bool inner = inner_cols && i > 0 && i < f.nx - 1;   // warp-uniform
-        float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
+        for (int s = 0; s < RING; ++s) {
+            const int i = ib + s;
+            if (i >= i1) break;                                   // warp-uniform
+            constexpr int UNUSED = 0; (void)UNUSED;
+            const int kup = s % RING, kmid = (s + 1) % RING, kdn = (s + 2) % RING, knew = (s + 4) % RING;
+            {
+                const int d = 3 * f.ny;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            const float* t = a.map[m];
-            float lf = __shfl_up_sync(FULL_MASK, mid[m], 1);
-            float rt = __shfl_down_sync(FULL_MASK, mid[m], 1);
-            if (edge_lane) {   // one predicated load serves both ends of the strip
-                const float h = __ldg(t + offh);
-                if (lane == 0) lf = h; else rt = h;
-            }
-            float gy, gx;
-            if (inner) {
-                gy = rt - lf;
-                gx = dn[m] - up[m];
-            } else {
-                // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
-                const float* r = t + (size_t)i * f.ny;
-                if (jc == 0) gy = -3.f * mid[m] + 4.f * rt - __ldg(r + 2);
-                else if (jc == f.ny - 1) gy = 3.f * mid[m] - 4.f * lf + __ldg(r + f.ny - 3);
-                else gy = rt - lf;
-                if (i == 0) gx = -3.f * mid[m] + 4.f * dn[m] - __ldg(t + (size_t)2 * f.ny + jc);
-                else if (i == f.nx - 1) gx = 3.f * mid[m] - 4.f * up[m] + __ldg(t + (size_t)(f.nx - 3) * f.ny + jc);
-                else gx = dn[m] - up[m];
-            }
-            dxo = fmaf(a.g_obj[m], gx, dxo);
-            dyo = fmaf(a.g_obj[m], gy, dyo);
-            if (DUAL) {
-                dxr = fmaf(a.g_ref[m], gx, dxr);
-                dyr = fmaf(a.g_ref[m], gy, dyr);
-            }
-            if (ATT) arg = fmaf(a.att[m], mid[m], arg);
-        }
-        float vo = ATT ? vin * expf(-arg) : vin;   // Sample.py:347
-        float vr = vin;
-        if (live) {
-            if (a.zero[0]) a.zero[0][off] = 0.f;
-            if (a.zero[1]) a.zero[1][off] = 0.f;
-            if (a.zero[2]) a.zero[2][off] = 0.f;
-            if (HAS_I && a.clear_input) const_cast<float*>(a.I_in)[off] = 0.f;
-        }
-        {
-            // A `simple` ray lands strictly inside the image, so |D| < N: the kill rule of
-            // refractionFileNumba2.py:61-64 cannot fire, and the |D| < 1e-12 -> 0 rule (:59-60) changes
-            // nothing at fp32 resolution.  Everything else is cleaned and takes the reference's edge rules.
-            const TileRay q = tile_ray(i, j, vo, dxo, dyo, f.nx, f.ny);
-            const bool fast = inner_cols && __all_sync(FULL_MASK, q.simple);
-            if (fast) sp_obj.put(q);
-            else {
-                clean(vo, dxo, dyo, a.clamp_x, a.clamp_y);
-                slow_obj.put(live ? make_ray(i, j, vo, dxo, dyo, f) : empty_ray());
-            }
-            if (DUAL) {
-                // outside the sample the two beams are the same ray: form it once, deposit it twice
-                const bool same = fast && __all_sync(FULL_MASK, dxo == dxr && dyo == dyr && vo == vr);
-                if (same) {
-                    sp_ref.put(q);
-                    ref_sum += vr;
-                } else {
-                    const TileRay qr = tile_ray(i, j, vr, dxr, dyr, f.nx, f.ny);
-                    if (inner_cols && __all_sync(FULL_MASK, qr.simple)) {
-                        sp_ref.put(qr);
-                        ref_sum += vr;
-                    } else {
-                        clean(vr, dxr, dyr, a.clamp_x, a.clamp_y);
-                        const Ray qs = live ? make_ray(i, j, vr, dxr, dyr, f) : empty_ray();
-                        slow_ref.put(qs);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) ref_sum += ((qs.ok >> k) & 1u) ? qs.w[k] : 0.f;
-                    }
+                for (int m = 0; m < NM; ++m) {
+                    row[knew][m] = __ldg(a.map[m] + min(off + d, last + jc));
+                    hal[knew][m] = edge_lane ? __ldg(a.map[m] + min(offh + d, last + jh)) : 0.f;
                 }
+                inten[knew] = HAS_I ? a.I_in[min(off + d, last + jc)] : a.I_uniform;
             }
-        }
+            const bool inner = inner_cols && i > 0 && i < f.nx - 1;   // warp-uniform
+            float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) { up[m] = mid[m]; mid[m] = dn[m]; dn[m] = n1[m]; n1[m] = n2[m]; }
-        vin = vn1; vn1 = vn2;
-        off += f.ny; offh += f.ny;
+            for (int m = 0; m < NM; ++m) {
+                const float* t = a.map[m];
+                const float mid = row[kmid][m], up = row[kup][m], dn = row[kdn][m];
+                float lf = __shfl_up_sync(FULL_MASK, mid, 1);
+                float rt = __shfl_down_sync(FULL_MASK, mid, 1);
+                if (lane == 0) lf = hal[kmid][m];
+                if (lane == 31) rt = hal[kmid][m];
+                float gy, gx;
+                if (inner) {
+                    gy = rt - lf;
+                    gx = dn - up;
+                } else {
+                    // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
+                    const float* r = t + (size_t)i * f.ny;
+                    if (jc == 0) gy = -3.f * mid + 4.f * rt - __ldg(r + 2);
+                    else if (jc == f.ny - 1) gy = 3.f * mid - 4.f * lf + __ldg(r + f.ny - 3);
+                    else gy = rt - lf;
+                    if (i == 0) gx = -3.f * mid + 4.f * dn - __ldg(t + (size_t)2 * f.ny + jc);
+                    else if (i == f.nx - 1) gx = 3.f * mid - 4.f * up + __ldg(t + (size_t)(f.nx - 3) * f.ny + jc);
+                    else gx = dn - up;
+                }
+                dxo = fmaf(a.g_obj[m], gx, dxo);
+                dyo = fmaf(a.g_obj[m], gy, dyo);
+                if (DUAL) {
+                    dxr = fmaf(a.g_ref[m], gx, dxr);
+                    dyr = fmaf(a.g_ref[m], gy, dyr);
+                }
+                if (ATT) arg = fmaf(a.att[m], mid, arg);
+            }
+            const float vin = inten[kmid];
+            // Sample.py:347; ex2.approx keeps ~2e-7 relative accuracy over the attenuation range
+            const float vo = ATT ? vin * ex2_fast(arg * neg_log2e) : vin;
+            if (live) {
+                if (zero_fill) { a.zero[0][off] = 0.f; a.zero[1][off] = 0.f; a.zero[2][off] = 0.f; }
+                if (clear_in) const_cast<float*>(a.I_in)[off] = 0.f;
+            }
+            deposit<SC>(tobj, i, j, vo, dxo, dyo, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+            if (DUAL) ref_sum += deposit<SC>(tref, i, j, vin, dxr, dyr, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+            off += f.ny; offh += f.ny;
+        }
     }
-    const bool bad = sp_obj.bad | slow_obj.bad | (DUAL && (sp_ref.bad | slow_ref.bad));
     if (bad && a.flag) atomicOr(a.flag, FLAG_NONFINITE);
     if (DUAL && a.sum_ref) {   // one double atomic per warp
 #pragma unroll
@@ -266,21 +246,44 @@ refract_tile_kernel(const RefractArgs<float> a) {
     __syncthreads();
     const bool vec_ok = (f.ny & 3) == 0;
     const float inv_scale = a.intensity_scale / (float)(1u << FIX_BITS);
-    flush_tile<SR, SC>(tobj, a.out_obj, rlo, clo, f.nx, f.ny, inv_scale, vec_ok && (reinterpret_cast<uintptr_t>(a.out_obj) & 15) == 0);
-    if (DUAL) flush_tile<SR, SC>(tref, a.out_ref, rlo, clo, f.nx, f.ny, inv_scale, vec_ok && (reinterpret_cast<uintptr_t>(a.out_ref) & 15) == 0);
+    flush_tile<SR, SC>(tobj.tile, a.out_obj, tobj.rlo, tobj.clo, f.nx, f.ny, inv_scale, vec_ok && (reinterpret_cast<uintptr_t>(a.out_obj) & 15) == 0);
+    if (DUAL) flush_tile<SR, SC>(tref.tile, a.out_ref, tobj.rlo, tobj.clo, f.nx, f.ny, inv_scale, vec_ok && (reinterpret_cast<uintptr_t>(a.out_ref) & 15) == 0);
+}
+
+// Rows per block: all blocks cost the same, so a launch takes ceil(blocks / resident slots) rounds.  Pick the row count
+// (<= TR, the size the tile was built for) whose last round is fullest, charging the fixed cost of a block (three
+// extra thickness rows, halo flush) against short tiles.
+inline int pick_tile_rows(int nx, int strips, int slots, int max_rows) {
+    int best = max_rows;
+    double best_score = -1.0;
+    for (int rows = max_rows; rows >= 6; --rows) {
+        const long blocks = (long)strips * div_up(nx, rows);
+        const long rounds = (blocks + slots - 1) / slots;
+        const double score = (double)blocks / (double)(rounds * slots) * rows / (rows + 4.0);
+        if (score > best_score + 1e-9) { best_score = score; best = rows; }
+    }
+    return best;
 }
 
 template <int NM, bool DUAL, bool HAS_I, bool ATT, int TR, int H>
-static int launch_refract_tile(const RefractArgs<float>& a, cudaStream_t s) {
+static int launch_refract_tile(const RefractArgs<float>& a_in, cudaStream_t s) {
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     constexpr size_t smem = sizeof(unsigned) * SR * SC * (DUAL ? 2 : 1);
-    static bool configured = false;
-    if (!configured) {
+    static int slots = 0;
+    if (!slots) {
         PARESIS_CUDA(cudaFuncSetAttribute(refract_tile_kernel<NM, DUAL, HAS_I, ATT, TR, H>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        int per_sm = 0, dev = 0, sms = 0;
+        PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refract_tile_kernel<NM, DUAL, HAS_I, ATT, TR, H>,
+                                                                   TILE_COLS, smem));
+        PARESIS_CUDA(cudaGetDevice(&dev));
+        PARESIS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        slots = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
-    dim3 grid(div_up(a.f.ny, TILE_COLS), div_up(a.f.nx, TR));
+    RefractArgs<float> a = a_in;
+    const int strips = div_up(a.f.ny, TILE_COLS);
+    a.rows = pick_tile_rows(a.f.nx, strips, slots, TR);
+    dim3 grid(strips, div_up(a.f.nx, a.rows));
     refract_tile_kernel<NM, DUAL, HAS_I, ATT, TR, H><<<grid, TILE_COLS, smem, s>>>(a);
     PARESIS_LAUNCH_CHECK("refract_tile_kernel");
     return PARESIS_OK;

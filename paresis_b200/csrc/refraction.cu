@@ -363,7 +363,10 @@ extern "C" int paresis_refract_layers_ex(const float* intensity_in, float intens
     a.flag = flag;
     cudaStream_t s = (cudaStream_t)stream;
     if (extras) {
-        for (int k = 0; k < 3; ++k) a.zero[k] = extras->zero_fill[k];
+        // compact the zero-fill list; kernels that test only slot 0 get every slot filled (a repeated store is harmless)
+        int nz = 0;
+        for (int k = 0; k < 3; ++k) if (extras->zero_fill[k]) a.zero[nz++] = extras->zero_fill[k];
+        for (int k = nz; k < 3 && nz > 0; ++k) a.zero[k] = a.zero[0];
         a.clear_input = extras->clear_input != 0 && intensity_in != nullptr;
         a.sum_ref = out_ref ? extras->sum_ref : nullptr;
         a.zero_scalar = extras->zero_scalar;
