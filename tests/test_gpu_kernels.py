@@ -297,3 +297,114 @@ def test_poisson_statistics(abi):
     d = torch.empty(1000, device="cuda")
     abi.poisson(lam[:1000].contiguous(), d, 5, 1)
     assert torch.equal(d, a[:1000])
+
+
+@pytest.mark.parametrize("shape", [(130, 290), (300, 257), (40, 36), (517, 1030)])
+def test_tile_hop_kernel_matches_direct_kernel(abi, shape):
+    """The fixed-point shared-memory tile kernel (intensity_scale given) against the fp32 direct-to-L2
+    kernel on the same inputs: membrane-like torn field, rays brighter than 2 x scale, negative rays,
+    ragged / odd sizes; plus the pipeline extras (zero-fill, clear-input, reference-beam sum)."""
+    rng = np.random.default_rng(5)
+    x = np.linspace(0, 9, shape[0])[:, None]
+    y = np.linspace(0, 9, shape[1])[None, :]
+    caps = np.sqrt(np.maximum(0.0, 0.2 - (np.mod(x, 1.0) - 0.5) ** 2 - (np.mod(y, 1.0) - 0.5) ** 2))   # torn gradients
+    t_mem = (6e-4 * caps).astype(np.float32)
+    t_smp = (9e-4 * np.exp(-((x - 4.5) ** 2 + (y - 4.2) ** 2))).astype(np.float32)
+    E, pix, M, d3 = 52.0, 2.9256, 1.0254, 3.6
+    g3m, _ = _layer_coeffs([5.97e-7], [5.37e-9], E, d3, M, pix)
+    g3s, a3s = _layer_coeffs([9.52e-8], [4.4e-11], E, d3, M, pix)
+    i0 = 7500.0
+    i_in = (i0 * (0.6 + 0.8 * rng.random(shape))).astype(np.float32)
+    i_in[rng.random(shape) > 0.995] *= 4.0          # brighter than 2 x intensity_scale: fp32 path
+    i_in[3, 5] = -10.0                              # negative: fp32 path
+    layers = [(dev(t_mem), g3m[0], g3m[0], 0.0), (dev(t_smp), g3s[0], 0.0, a3s[0])]
+    ref_s = torch.zeros(shape, device="cuda"); ref_r = torch.zeros(shape, device="cuda")
+    abi.refract_layers(dev(i_in), 0.0, layers, ref_s, ref_r)
+    src = dev(i_in)
+    out_s = torch.zeros(shape, device="cuda"); out_r = torch.zeros(shape, device="cuda")
+    junk = [torch.full(shape, 3.0, device="cuda") for _ in range(2)]
+    total = torch.full((1,), 5.0, device="cuda", dtype=torch.float64)
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    abi.refract_layers(src, 0.0, layers, out_s, out_r, flag=flag, zero_fill=junk, clear_input=True, sum_ref=total,
+                       intensity_scale=i0)
+    assert int(flag.item()) == 0
+    assert rel_l2(out_s.cpu().numpy(), ref_s.cpu().numpy()) < 3e-6
+    assert rel_l2(out_r.cpu().numpy(), ref_r.cpu().numpy()) < 3e-6
+    assert not src.any() and not junk[0].any() and not junk[1].any()
+    assert abs((total.item() - 5.0) / ref_r.double().sum().item() - 1) < 1e-6
+    # single beam, uniform input (the membrane hop), with the scalar zeroed by the kernel
+    one_ref = torch.zeros(shape, device="cuda"); one = torch.zeros(shape, device="cuda")
+    abi.refract_layers(None, i0, [(dev(t_mem), g3m[0], 0.0, a3s[0])], one_ref)
+    abi.refract_layers(None, i0, [(dev(t_mem), g3m[0], 0.0, a3s[0])], one, zero_scalar=total, intensity_scale=i0)
+    assert rel_l2(one.cpu().numpy(), one_ref.cpu().numpy()) < 3e-6 and total.item() == 0.0
+    # a NaN intensity is reported, as the reference's guard does (refractionFileNumba2.py:81-82)
+    bad = i_in.copy(); bad[shape[0] // 2, shape[1] // 2] = np.nan
+    abi.refract_layers(dev(bad), 0.0, layers, out_s, out_r, flag=flag, intensity_scale=i0)
+    assert int(flag.item()) & abi.FLAG_NONFINITE
+
+
+def test_tile_hop_kernel_cannot_overflow(abi):
+    """Every ray of a tile focused into ONE cell (a lens): the fixed-point tile holds it (rays per tile x
+    brightest fixed-point ray < 2^32) and the image gets the exact sum."""
+    n = 256
+    i = np.arange(n, dtype=np.float64)
+    # parabolic thickness: gradient proportional to the distance from the centre -> all rays land at the centre
+    E, pix, M, d3 = 52.0, 2.9256, 1.0254, 3.6
+    g, _ = _layer_coeffs([1.0], [0.0], E, d3, M, pix)          # pixels per metre of 2-pixel difference
+    c = (n - 1) / 2
+    t = -(((i[:, None] - c) ** 2 + (i[None, :] - c) ** 2) / (4 * g[0]))    # D = g * (t[+1]-t[-1]) = (c - i)
+    tm = dev(t.astype(np.float32))
+    i0 = 1000.0
+    out = torch.zeros((n, n), device="cuda"); ref = torch.zeros((n, n), device="cuda")
+    abi.refract_layers(None, 1.9 * i0, [(tm, g[0], 0.0, 0.0)], out, intensity_scale=i0)
+    abi.refract_layers(None, 1.9 * i0, [(tm, g[0], 0.0, 0.0)], ref)
+    assert abs(out.double().sum().item() / ref.double().sum().item() - 1) < 1e-6
+    assert out.max().item() > 0.2 * n * n * 1.9 * i0          # really focused
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_membrane_from_field_matches_raster(abi):
+    """Positions cut from the once-rasterised sphere field = positions rasterised one by one."""
+    from ref_harness import synthetic_sphere_rows
+    rows = synthetic_sphere_rows(0, 60000)
+    mean_r, layers, dx, dy, pix = 50.0, 3, 300, 420, 2.853
+    tab, ex, ey = po.membrane_sphere_table(rows, mean_r, dx, dy, pix)
+    margin, margin2 = po.membrane_margin(mean_r, pix)
+    table = dev(tab, torch.float64)
+    reach = int(np.floor(tab[:, 2].max() / pix)) + 1
+    assert reach <= margin2
+    field = torch.empty((int(np.ceil(ex / pix)) + margin + 1, int(np.ceil(ey / pix)) + margin + 1), device="cuda")
+    abi.raster_field(table, pix, field)
+    np.random.seed(3)
+    for _ in range(3):
+        offs = po.draw_membrane_offsets(layers, mean_r, ex, ey, dx, dy, pix)
+        a = torch.empty((dx, dy), device="cuda"); b = torch.full((dx, dy), -1.0, device="cuda")
+        abi.raster_spheres(table, pix, offs, dx, dy, margin, a)
+        abi.membrane_from_field(field, offs, margin, dx, dy, b)
+        assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+
+
+def test_detector_images_in_one_launch(abi, golden):
+    """paresis_detect_counts_multi = paresis_detect_counts image by image (same Poisson streams)."""
+    from paresis_b200 import hostmath as hm
+    g = golden("detector")
+    for kcase in range(int(g["n_det"])):
+        os_, d0, d1, fwhm, psf = g["det%d_cfg" % kcase]
+        os_, d0, d1 = int(os_), int(d0), int(d1)
+        imgs = [dev(g["det%d_in" % kcase]), dev(np.abs(g["det%d_in" % kcase][::-1].copy()) + 3.0)]
+        src = dev(hm.gaussian_1d(fwhm / 2.355)) if fwhm != 0 else None
+        pk = dev(hm.gaussian_1d(psf)) if psf != 0 else None
+        for noise in (False, True):
+            single = [torch.empty((d0, d1), device="cuda") for _ in imgs]
+            multi = [torch.empty((d0, d1), device="cuda") for _ in imgs]
+            for k, im in enumerate(imgs):
+                abi.detect_counts(im, os_, d0, d1, src, pk, None, single[k], noise, 11, 100 + k)
+            abi.detect_counts_multi(imgs, os_, d0, d1, src, pk, None, multi, noise, 11, [100, 101])
+            for s, m in zip(single, multi):
+                assert torch.equal(s, m), (kcase, noise)
+            if noise:
+                # ... and the fused draw is the stand-alone sampler applied to the expectation
+                expect = torch.empty((d0, d1), device="cuda"); counts = torch.empty((d0, d1), device="cuda")
+                abi.detect_counts(imgs[1], os_, d0, d1, src, pk, None, expect, False)
+                abi.poisson(expect, counts, 11, 101)
+                assert torch.equal(counts, multi[1]), kcase
