@@ -46,7 +46,7 @@ ALG_BYTES = {
     "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
     "detect": lambda n, det: 2 * (4.0 * n + 4.0 * det),       # sample + reference images in one launch: read, write counts
 }
-SLOTS = 2   # positions in flight (paresis_rt_run_positions deals them over this many streams)
+SLOTS = 3   # positions in flight (paresis_rt_run_positions deals them over this many streams)
 
 
 def config_dict(**extra):
@@ -243,8 +243,12 @@ def run_gpu(args):
         offsets = [plan.draw_offsets() for _ in points]         # the reference's randint draws, in its order
         pe = None
         if probe_label is not None:
-            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in points]
-            events.extend(pe)
+            # all positions when profiling one at a time; ONE position per step in the timed region (it runs alone
+            # on the GPU for that moment, see paresis_rt_position.probe_start)
+            probed = points if (slots or args.slots) == 1 else [POSITIONS // 2]
+            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if p in probed else None
+                  for p in points]
+            events.extend(e for e in pe if e is not None)
         with abi.on_stream():
             res = eng.compute_rt_positions(scene, plan, offsets, points, sequence_base=step * POSITIONS,
                                            n_slots=slots or args.slots, probe_label=probe_label, probe_events=pe,
@@ -332,6 +336,10 @@ def run_gpu(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg = ALG_BYTES[dominant](n * n, det * det)
+        traffic = None
+        traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")     # dram__bytes_{read,write}.sum of one ncu capture
+        if os.path.exists(traffic_path):
+            traffic = json.load(open(traffic_path)).get(dominant, {}).get("dram_bytes")
         avg_ms = float(np.mean(k_ms)) if k_ms else shares[dominant]["ms_per_launch"]
         achieved = alg / (avg_ms * 1e-3) / 1e9
         line = {
@@ -346,11 +354,10 @@ def run_gpu(args):
                     "pinned_buffers_allocated": transfer.pinned_allocs},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_timed": len(k_ms),
-                         "note": "timed live in the timed region with %d positions in flight (kernels of neighbouring "
-                                 "positions share the SMs); kernel_shares holds the same kernels timed one position at a time"
-                                 % args.slots},
+                         "note": "CUDA events around the kernel of one position per timed step; that position runs alone on "
+                                 "the GPU (the other %d in flight drain first), so the interval is this kernel only" % (args.slots - 1)},
             "kernel_shares": shares,
         }
         if world == 1 and not args.no_cpu_baseline:

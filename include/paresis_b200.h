@@ -186,7 +186,8 @@ typedef struct {
     double* means;                 /* [n_energies] or NULL */
     uint64_t sequence;
     int first_point;
-    void* probe_start; void* probe_end;   /* optional cudaEvent_t pair for job_host->probe (4 = the membrane raster) */
+    void* probe_start; void* probe_end;   /* optional cudaEvent_t pair for job_host->probe (4 = the membrane raster);
+                                             a probed position runs alone: the other slots drain first and wait for it */
 } paresis_rt_position;
 
 typedef struct {

@@ -21,6 +21,9 @@
 namespace paresis {
 
 constexpr int DT_TX = 32, DT_TY = 64, DT_THREADS = 256;
+#ifndef DT_MIN_BLOCKS
+#define DT_MIN_BLOCKS 4
+#endif
 
 template <int OS, int HS, int HP>
 struct DetTile {
@@ -45,7 +48,7 @@ struct DetTile {
 };
 
 template <int OS, int HS, int HP>
-__global__ void __launch_bounds__(DT_THREADS)
+__global__ void __launch_bounds__(DT_THREADS, DT_MIN_BLOCKS)
 detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const float* __restrict__ gsrc,
                    const float* __restrict__ gpsf, int noise, uint64_t seed) {
     using T = DetTile<OS, HS, HP>;

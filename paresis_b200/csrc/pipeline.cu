@@ -147,6 +147,16 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
             set_last_error("paresis_rt_run_positions: position %d lacks offsets or a thickness buffer", p);
             return PARESIS_ERR_ARG;
         }
+        // A probed position runs alone on the GPU (the other slots drain first and wait for it), so that the
+        // CUDA events around its kernel time that kernel and not its neighbours on the other streams.
+        const bool probed = job->probe != 0 && pos.probe_start && pos.probe_end && n_slots > 1;
+        if (probed) {
+            for (int k = 0; k < used; ++k) {
+                if (&slots[k] == &slot) continue;
+                PARESIS_CUDA(cudaEventRecord(g_events.join[k], (cudaStream_t)slots[k].stream));
+                PARESIS_CUDA(cudaStreamWaitEvent((cudaStream_t)slot.stream, g_events.join[k], 0));
+            }
+        }
         const bool probe_raster = job->probe == 4 && pos.probe_start && pos.probe_end;
         if (probe_raster) cudaEventRecord((cudaEvent_t)pos.probe_start, (cudaStream_t)slot.stream);
         if (mem->field)
@@ -182,6 +192,11 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
         rc = paresis_rt_run(&j, slot.stream);
         if (rc) return rc;
         slot.i_bs_dirty = 0;
+        if (probed) {
+            PARESIS_CUDA(cudaEventRecord(g_events.fork, (cudaStream_t)slot.stream));
+            for (int k = 0; k < used; ++k)
+                if (&slots[k] != &slot) PARESIS_CUDA(cudaStreamWaitEvent((cudaStream_t)slots[k].stream, g_events.fork, 0));
+        }
     }
     for (int k = 0; k < used; ++k) {
         PARESIS_CUDA(cudaEventRecord(g_events.join[k], (cudaStream_t)slots[k].stream));

@@ -353,7 +353,7 @@ class ImageFormation:
             cp.means = buffers["sums"][p].data_ptr() if want_means else None
             cp.sequence = self.sequence(points[p], sequence_base)
             cp.first_point = 1 if first else 0
-            if probe_events is not None:
+            if probe_events is not None and probe_events[p] is not None:
                 e0, e1 = probe_events[p]
                 for e in (e0, e1):
                     if not e.cuda_event:
