@@ -256,7 +256,7 @@ refract_tile_kernel(const RefractArgs<float> a) {
 inline int pick_tile_rows(int nx, int strips, int slots, int max_rows) {
     int best = max_rows;
     double best_score = -1.0;
-    for (int rows = max_rows; rows >= 6; --rows) {
+    for (int rows = max_rows; rows >= (max_rows > 8 ? 6 : 4); --rows) {
         const long blocks = (long)strips * div_up(nx, rows);
         const long rounds = (blocks + slots - 1) / slots;
         const double score = (double)blocks / (double)(rounds * slots) * rows / (rows + 4.0);

@@ -249,7 +249,7 @@ static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
     const bool dual = a.out_ref != nullptr, has_i = a.I_in != nullptr;
     const bool wd = a.dx_pad != nullptr;
     if (!wd && g_tile_config == 2 && (a.f.ny & 1) == 0 && pair_aligned(a)) return dispatch_refract_pair(NM, a, g_rows_override, s);
-    if (!wd && (g_tile_config == 0 || g_tile_config == 1) && a.intensity_scale > 0.f) return dispatch_refract_tile(NM, a, g_tile_config, s);
+    if (!wd && (g_tile_config == 0 || g_tile_config == 1 || g_tile_config == 3) && a.intensity_scale > 0.f) return dispatch_refract_tile(NM, a, g_tile_config, s);
     if (dual) return has_i ? launch_refract<float, NM, true, true, true>(a, false, s)
                            : launch_refract<float, NM, true, false, true>(a, false, s);
     return has_i ? launch_refract<float, NM, false, true, true>(a, wd, s)
@@ -264,7 +264,7 @@ extern "C" int paresis_set_tuning(int key, int value) {
     switch (key) {
         case 0: g_fused_mode = value == 0 ? 0 : 2; return PARESIS_OK;
         case 1: g_rows_override = value; return PARESIS_OK;
-        case 2: g_tile_config = value < 0 ? -1 : (value > 2 ? 2 : value); return PARESIS_OK;
+        case 2: g_tile_config = value < 0 ? -1 : (value > 3 ? 3 : value); return PARESIS_OK;
         default: set_last_error("paresis_set_tuning: unknown key %d", key); return PARESIS_ERR_ARG;
     }
 }
