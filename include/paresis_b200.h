@@ -328,6 +328,14 @@ int paresis_cylinder_map(double radius_um, double angle_deg, int dim_x, int dim_
 /* ---------------------------------------------------------------------------------------
  * Small utilities used by the host shim
  * ------------------------------------------------------------------------------------- */
+/* Result transfers (the reference hands back host arrays: Experiment.py:405, :526, main.py:99): an
+ * asynchronous device -> pinned-host copy on the library's copy stream, ordered after `producer`.
+ * A lane holds the events of one copy in flight; reuse it once paresis_transfer_wait returned. */
+int paresis_transfer_lane_create(void** lane_out);
+int paresis_transfer_lane_destroy(void* lane);
+int paresis_transfer_d2h(void* lane, void* dst_host_pinned, const void* src_device, size_t bytes, paresis_stream producer);
+int paresis_transfer_wait(void* lane);
+
 int paresis_fill(float* dst, float value, size_t n, paresis_stream stream);
 int paresis_axpy(float* dst, const float* src, float scale, size_t n, paresis_stream stream); /* dst += scale*src */
 /* mean of an image (np.mean at Experiment.py:485-486), result to a device double */

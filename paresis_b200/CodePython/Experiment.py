@@ -253,12 +253,19 @@ class Experiment:
                                                  seed=det.seed, poisson=det.poissonNoise)
         return self._engine
 
-    def _finish(self, res):
+    def _finish(self, res, scene=None):
         """Device images -> the float64 [nbins, dimX, dimY] arrays the reference returns; images that were
         not computed (propagation / white beyond point 0) are zeros, as upstream (Experiment.py:433-434)."""
-        num, den = res["mean_energy"]
+        images = transfer.Pending(res["_stack"], torch.float64)    # one cast + one PCIe copy for all images
+        if "aux" in res:
+            # deferred bookkeeping: the per-energy sums and the status flag ride behind the images
+            aux = transfer.Pending(res["aux"])
+            host = images.wait()
+            num, den = self._get_engine().finish_deferred(scene, aux.wait())
+        else:
+            host = images.wait()
+            num, den = res["mean_energy"]
         self.exp_dict['meanEnergy'] = (self.exp_dict['meanEnergy'] + num) / den      # Experiment.py:486, :523
-        host = transfer.fetch(res["_stack"], torch.float64)       # one cast + one PCIe copy for all images
         out = [host[i] for i in range(host.shape[0])]
         while len(out) < 4:
             out.append(self._zeros(out[0].shape))
@@ -304,11 +311,12 @@ class Experiment:
             print("Current Energy: %gkev" % energy)
         eng = self._get_engine()
         want_d = pointNum == 0 and bool(self.exp_dict.get("returnDisplacement", True))
+        scene = self._scene(thresholds)
         try:
-            res = eng.compute_rt(self._scene(thresholds), pointNum, want_displacement=want_d)
+            res = eng.compute_rt(scene, pointNum, want_displacement=want_d, defer=True)
+            out = self._finish(res, scene)
         except engine.InsaneValues as exc:
             raise Exception(str(exc))
-        out = self._finish(res)
         if want_d:
             self.Dxreal = transfer.fetch(eng.dx_pad, torch.float64)
             self.Dyreal = transfer.fetch(eng.dy_pad, torch.float64)

@@ -27,6 +27,7 @@ EXPORTS = (
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
+    "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
 
@@ -128,6 +129,10 @@ def _load():
         "paresis_mean": [vp, sz, vp, vp],
         "paresis_sum_scaled": [vp, sz, cd, vp, vp],
         "paresis_rt_run": [ctypes.POINTER(RtJob), vp],
+        "paresis_transfer_lane_create": [ctypes.POINTER(vp)],
+        "paresis_transfer_lane_destroy": [vp],
+        "paresis_transfer_d2h": [vp, vp, vp, sz, vp],
+        "paresis_transfer_wait": [vp],
         "paresis_rt_run_positions": [ctypes.POINTER(RtJob), ctypes.POINTER(Membrane), ctypes.POINTER(RtPosition), ci,
                                      ctypes.POINTER(RtSlot), ci, vp],
         "paresis_refract_layers_ex": [vp, cf, ctypes.POINTER(Layer), ci, vp, vp, vp, vp, ci, ci, ci, vp,

@@ -243,7 +243,8 @@ class ImageFormation:
         """Poisson stream id of a position; image k of bin b draws from sequence + 4b + k."""
         return (sequence_base + point_num) << 16
 
-    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True):
+    def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True,
+                   defer=False):
         """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526) as one library
         call (paresis_rt_run).
 
@@ -269,10 +270,23 @@ class ImageFormation:
             job.dx_pad, job.dy_pad = self.dx_pad.data_ptr(), self.dy_pad.data_ptr()
         launches = n_e * (3 if first else 2) + len(closing) * (2 if first else 1)
         self._run(job, launches, probe)
-        if want_mean:
+        if want_mean and defer:
+            # no host synchronisation here: the per-energy sums and the status flag travel with the images
+            # (one small device buffer); the caller finishes with finish_deferred() once they are on the host
+            out["aux"] = torch.cat((self.means[:n_e], self.flag.to(torch.float64)))
+            self.flag.zero_()
+        elif want_mean:
             out["mean_energy"] = self._mean_energy([e for e, _ in s.spectrum], sums=self.means[:n_e].cpu().numpy())
             self.check_flag()
         return out
+
+    def finish_deferred(self, scene, aux_host):
+        """``aux_host`` = host copy of ``out["aux"]`` of a deferred compute_rt: -> mean_energy, raising the
+        reference's 'insane values' error if the status flag was set."""
+        aux = np.asarray(aux_host, dtype=np.float64)
+        if int(aux[-1]) & abi.FLAG_NONFINITE:
+            raise InsaneValues("The calculated intensity refractive includes some nans or insane values")
+        return self._mean_energy([e for e, _ in scene.spectrum], sums=aux[:-1])
 
     def _run(self, job, launches, probe=None):
         """paresis_rt_run keeps I_bs all-zero between jobs; a failed call may leave it dirty."""

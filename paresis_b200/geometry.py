@@ -174,9 +174,24 @@ class MembranePlan:
         return offsets
 
 
+_plans = {}
+
+
+def _plan(sample, dim_x, dim_y, pix):
+    """MembranePlan of this membrane, rebuilt when the sphere file or the geometry changes."""
+    st = os.stat(_MEMBRANE_FILE)
+    key = (sample.myMeanSphereRadius, sample.myNbOfLayers, int(dim_x), int(dim_y), float(pix), st.st_mtime_ns, st.st_size,
+           torch.cuda.current_device())
+    plan = _plans.get(key)
+    if plan is None or plan._field_key[0] != plan.table.data_ptr() or not _device_tables:
+        _plans.clear()
+        plan = _plans[key] = MembranePlan(sample, dim_x, dim_y, pix)
+    return plan
+
+
 def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):
     """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171)."""
-    plan = MembranePlan(sample, dim_x, dim_y, pix)
+    plan = _plan(sample, dim_x, dim_y, pix)
     offsets = plan.draw_offsets()
     dim_x, dim_y = plan.dim_x, plan.dim_y
     grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)

@@ -1,22 +1,24 @@
 """Device -> host result copies through pinned staging memory.
 
-``fetch`` returns a numpy array that is a zero-copy view of a pinned host tensor (torch's caching
-pinned allocator recycles the block once the array is garbage collected), filled by an
-asynchronous copy on a dedicated copy stream.  ``bytes_d2h`` / ``bytes_h2d`` count what crossed
-PCIe through this module (bench.py reports them).
+``fetch`` returns a numpy array that is a zero-copy view of a pinned host tensor, filled by an
+asynchronous copy on the library's copy stream (``paresis_transfer_d2h``: one C call per copy --
+event record, stream wait, cudaMemcpyAsync, event record).  ``bytes_d2h`` / ``bytes_h2d`` count what
+crossed PCIe through this module (bench.py reports them).
 """
+import ctypes
 import weakref
 
 import numpy as np
 import torch
 
+from . import _cabi as abi
+
 bytes_d2h = 0
 bytes_h2d = 0
-_copy_streams = {}
 
 # Pinned staging buffers are expensive to create (page locking: ~50 us per MiB), so they are
-# recycled: a buffer goes back to its pool when the numpy array handed to the caller -- and every
-# view of it -- has been garbage collected.
+# recycled together with their transfer lane (two CUDA events): a buffer goes back to its pool when
+# the numpy array handed to the caller -- and every view of it -- has been garbage collected.
 _pool = {}
 pinned_allocs = 0
 
@@ -28,20 +30,17 @@ def _pinned(shape, dtype):
     if free:
         return free.pop()
     pinned_allocs += 1
-    return torch.empty(shape, dtype=dtype, pin_memory=True)
+    lane = ctypes.c_void_p()
+    abi._check(abi.lib.paresis_transfer_lane_create(ctypes.byref(lane)), "paresis_transfer_lane_create")
+    return torch.empty(shape, dtype=dtype, pin_memory=True), lane
 
 
-def _release(key, tensor):
+def _release(key, entry):
     free = _pool.setdefault(key, [])
     if len(free) < 8:
-        free.append(tensor)
-
-
-def _copy_stream(device):
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in _copy_streams:
-        _copy_streams[key] = torch.cuda.Stream(device=key)
-    return _copy_streams[key]
+        free.append(entry)
+    else:
+        abi.lib.paresis_transfer_lane_destroy(entry[1])
 
 
 class Pending:
@@ -51,24 +50,23 @@ class Pending:
         global bytes_d2h
         if dtype is not None and tensor.dtype != dtype:
             tensor = tensor.to(dtype)               # cast on the device, on the producing stream
+        if not tensor.is_contiguous():
+            tensor = tensor.contiguous()
         self._src = tensor                          # keep alive until the copy is done
-        self.host = _pinned(tensor.shape, tensor.dtype)
-        ready = torch.cuda.Event()
-        ready.record()
-        stream = _copy_stream(tensor.device)
-        stream.wait_event(ready)
-        with torch.cuda.stream(stream):
-            self.host.copy_(tensor, non_blocking=True)
-            self.done = torch.cuda.Event()
-            self.done.record()
-        bytes_d2h += tensor.numel() * tensor.element_size()
+        self._key = (tuple(tensor.shape), tensor.dtype)
+        self.host, self.lane = _pinned(tensor.shape, tensor.dtype)
+        nbytes = tensor.numel() * tensor.element_size()
+        abi._check(abi.lib.paresis_transfer_d2h(self.lane, ctypes.c_void_p(self.host.data_ptr()),
+                                                ctypes.c_void_p(tensor.data_ptr()), nbytes, abi._stream()),
+                   "paresis_transfer_d2h")
+        bytes_d2h += nbytes
 
     def wait(self):
-        self.done.synchronize()
+        abi._check(abi.lib.paresis_transfer_wait(self.lane), "paresis_transfer_wait")
         self._src = None
         host, self.host = self.host, None
         arr = host.numpy()
-        weakref.finalize(arr, _release, (tuple(host.shape), host.dtype), host)
+        weakref.finalize(arr, _release, self._key, (host, self.lane))
         return arr
 
 
