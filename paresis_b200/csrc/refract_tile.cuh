@@ -143,11 +143,11 @@ refract_tile_kernel(const RefractArgs<float> a) {
         for (int k = threadIdx.x; k < NZ; k += TILE_COLS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // Row ring: slot k of step s holds row i-1+k; rows i-1, i, i+1 are used, row i+2 is in flight and row i+3 is
-    // fetched now.  The loop is unrolled by the ring size so that the rotation is register renaming -- a rotation by
+    // Row ring: slot k of step s holds row i-1+k; rows i-1, i, i+1 are used and row i+2 is fetched now (one full
+    // step ahead of its first use).  The loop is unrolled by the ring size so that the rotation is register renaming -- a rotation by
     // moves would wait for the load issued in the same step.  `hal` = the column next to the strip (edge lanes),
     // `inten` = the input intensity, same indexing.
-    constexpr int RING = 5;
+    constexpr int RING = 4;
     float row[RING][NM], hal[RING][NM], inten[RING];
     const bool edge_lane = lane == 0 || lane == 31;
     const int jh = min(max(lane == 0 ? jc - 1 : jc + 1, 0), f.ny - 1);
@@ -182,10 +182,9 @@ refract_tile_kernel(const RefractArgs<float> a) {
         for (int s = 0; s < RING; ++s) {
             const int i = ib + s;
             if (i >= i1) break;                                   // warp-uniform
-            constexpr int UNUSED = 0; (void)UNUSED;
-            const int kup = s % RING, kmid = (s + 1) % RING, kdn = (s + 2) % RING, knew = (s + 4) % RING;
+            const int kup = s % RING, kmid = (s + 1) % RING, kdn = (s + 2) % RING, knew = (s + 3) % RING;
             {
-                const int d = 3 * f.ny;
+                const int d = 2 * f.ny;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
                     row[knew][m] = __ldg(a.map[m] + min(off + d, last + jc));

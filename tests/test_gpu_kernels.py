@@ -358,7 +358,9 @@ def test_tile_hop_kernel_cannot_overflow(abi):
     out = torch.zeros((n, n), device="cuda"); ref = torch.zeros((n, n), device="cuda")
     abi.refract_layers(None, 1.9 * i0, [(tm, g[0], 0.0, 0.0)], out, intensity_scale=i0)
     abi.refract_layers(None, 1.9 * i0, [(tm, g[0], 0.0, 0.0)], ref)
-    assert abs(out.double().sum().item() / ref.double().sum().item() - 1) < 1e-6
+    # (the fp32 reference adds ~16k rays into each of four cells in scheduling order: its own sum moves by ~1e-6)
+    assert abs(out.double().sum().item() / ref.double().sum().item() - 1) < 1e-5
+    assert abs(out.double().sum().item() / (n * n * 1.9 * i0) - 1) < 2e-6    # the fixed-point path keeps the exact total
     assert out.max().item() > 0.2 * n * n * 1.9 * i0          # really focused
     assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
 
