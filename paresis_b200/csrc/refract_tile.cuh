@@ -52,9 +52,11 @@ struct TileTarget {
 // cells outside the image are dropped, which is what zero-padding, scattering and cropping does
 // (refractionFileNumba2.py:65-78; the |D| > N kill of :61-64 only removes rays that land outside anyway).
 // Returns what was deposited inside the image.
-template <int SC>
+// TWIN: the same ray goes to a second image as well (`t2`: its tile sits `twin_off` words after the first).
+template <int SC, bool TWIN>
 __device__ __forceinline__ float deposit(const TileTarget& t, int i, int j, float v, float dx, float dy, int nx, int ny,
-                                         float scale, unsigned vmax_bits, bool live, bool& bad) {
+                                         float scale, unsigned vmax_bits, bool live, bool& bad, float* out2 = nullptr,
+                                         int twin_off = 0) {
     const float flx = floorf(dx), fly = floorf(dy);
     const float fx = dx - flx, fy = dy - fly;
     const int r = i + __float2int_rd(dx), c = j + __float2int_rd(dy);   // saturating
@@ -66,10 +68,18 @@ __device__ __forceinline__ float deposit(const TileTarget& t, int i, int j, floa
         const float v1 = vs * fx, v0 = vs - v1;
         const float w1 = v0 * fy, w0 = v0 - w1, w3 = v1 * fy, w2 = v1 - w3;
         unsigned* p = t.tile + (r - t.rlo) * SC + (c - t.clo);
-        atomicAdd(p, __float2uint_rn(w0));
-        atomicAdd(p + 1, __float2uint_rn(w1));
-        atomicAdd(p + SC, __float2uint_rn(w2));
-        atomicAdd(p + SC + 1, __float2uint_rn(w3));
+        const unsigned u0 = __float2uint_rn(w0), u1 = __float2uint_rn(w1), u2 = __float2uint_rn(w2), u3 = __float2uint_rn(w3);
+        atomicAdd(p, u0);
+        atomicAdd(p + 1, u1);
+        atomicAdd(p + SC, u2);
+        atomicAdd(p + SC + 1, u3);
+        if (TWIN) {
+            unsigned* q = p + twin_off;
+            atomicAdd(q, u0);
+            atomicAdd(q + 1, u1);
+            atomicAdd(q + SC, u2);
+            atomicAdd(q + SC + 1, u3);
+        }
         return v;
     }
     float sum = 0.f;
@@ -79,11 +89,19 @@ __device__ __forceinline__ float deposit(const TileTarget& t, int i, int j, floa
         bad |= !(fabsf(w0 + w3) <= 3.0e38f);
         const bool ra = (unsigned)r < (unsigned)nx, rb = (unsigned)(r + 1) < (unsigned)nx;
         const bool ca = (unsigned)c < (unsigned)ny, cb = (unsigned)(c + 1) < (unsigned)ny;
-        float* p = t.out + (long long)r * ny + c;
+        const long long o = (long long)r * ny + c;
+        float* p = t.out + o;
         if (ra && ca && w0 != 0.f) { red_add(p, w0); sum += w0; }
         if (ra && cb && w1 != 0.f) { red_add(p + 1, w1); sum += w1; }
         if (rb && ca && w2 != 0.f) { red_add(p + ny, w2); sum += w2; }
         if (rb && cb && w3 != 0.f) { red_add(p + ny + 1, w3); sum += w3; }
+        if (TWIN) {
+            float* q = out2 + o;
+            if (ra && ca && w0 != 0.f) red_add(q, w0);
+            if (ra && cb && w1 != 0.f) red_add(q + 1, w1);
+            if (rb && ca && w2 != 0.f) red_add(q + ny, w2);
+            if (rb && cb && w3 != 0.f) red_add(q + ny + 1, w3);
+        }
     }
     return sum;
 }
@@ -231,8 +249,18 @@ refract_tile_kernel(const RefractArgs<float> a) {
                 if (zero_fill) { a.zero[0][off] = 0.f; a.zero[1][off] = 0.f; a.zero[2][off] = 0.f; }
                 if (clear_in) const_cast<float*>(a.I_in)[off] = 0.f;
             }
-            deposit<SC>(tobj, i, j, vo, dxo, dyo, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
-            if (DUAL) ref_sum += deposit<SC>(tref, i, j, vin, dxr, dyr, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+            if (DUAL) {
+                // outside the sample the two beams are the same ray: form it once, deposit it twice
+                const bool same = dxo == dxr && dyo == dyr && vo == vin;
+                if (__all_sync(FULL_MASK, same)) {
+                    ref_sum += deposit<SC, true>(tobj, i, j, vo, dxo, dyo, f.nx, f.ny, fix_scale, vmax_bits, live, bad, a.out_ref, SR * SC);
+                } else {
+                    deposit<SC, false>(tobj, i, j, vo, dxo, dyo, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+                    ref_sum += deposit<SC, false>(tref, i, j, vin, dxr, dyr, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+                }
+            } else {
+                deposit<SC, false>(tobj, i, j, vo, dxo, dyo, f.nx, f.ny, fix_scale, vmax_bits, live, bad);
+            }
             off += f.ny; offh += f.ny;
         }
     }

@@ -121,3 +121,37 @@ def test_polychromatic_configs_run_at_full_size(shim, name, n, energies):
     assert inner.std() / inner.mean() > 0.02                       # speckle
     assert sample[0, 64:-64, 64:-64].sum() < inner.sum()            # the fibre absorbs
     assert np.isfinite(sample).all() and (sample >= 0).all()
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_fresnel_against_refraction_model_at_full_size(shim, n, capsys):
+    """BASELINE.json config 4: the Fresnel propagator and the ray-tracing model on the same membrane and
+    sample, noise off.  The two models legitimately differ in the fine speckle structure (PARESIS UserGuide,
+    'Additional remarks'), so this is a physics cross-check, not a parity gate: same flux, same large-scale
+    image, correlated speckle; the relative L2 distance is printed for the record."""
+    out = {}
+    for model in ("RayT", "Fresnel"):
+        d = dict(experimentName="B200_%d_mono" % n, filepath="unused/", overSampling=2, nbExpPoints=1,
+                 simulation_type=model, expID="t", poissonNoise=False, returnDisplacement=False)
+        e = shim.Experiment(d)
+        assert tuple(e.exp_dict['studyDimensions']) == (n, n)
+        mem = e.myMembrane
+        np.random.seed(11)
+        mem.myGeometry = []
+        mem.getMyGeometry(e.exp_dict['studyDimensions'], mem.membranePixelSize, 2, 0, 1)
+        res = e.computeSampleAndReferenceImages_RT(0) if model == "RayT" else e.computeSampleAndReferenceImages_Fresnel(0)
+        out[model] = [np.asarray(r[0], dtype=np.float64) for r in res[:4]]
+        del e
+    for k, name in enumerate(("sample", "reference", "propagation", "white")):
+        a, b = out["RayT"][k][64:-64, 64:-64], out["Fresnel"][k][64:-64, 64:-64]
+        assert np.isfinite(b).all()
+        assert abs(b.mean() / a.mean() - 1) < 0.02, name                       # same flux
+        if name != "white":
+            # same image once the speckle grains (~17 detector pixels) are averaged over 64 x 64 pixels
+            m = (a.shape[0] // 64) * 64
+            ca = a[:m, :m].reshape(m // 64, 64, m // 64, 64).mean(axis=(1, 3))
+            cb = b[:m, :m].reshape(m // 64, 64, m // 64, 64).mean(axis=(1, 3))
+            assert rel_l2(cb, ca) < 0.05, name
+        with capsys.disabled():
+            print("\n[config 4, %d^2] %s: rel L2 Fresnel vs RayT = %.3f, correlation = %.3f"
+                  % (n, name, rel_l2(b, a), np.corrcoef(a.ravel()[::17], b.ravel()[::17])[0, 1] if a.std() > 0 else 1.0))
