@@ -328,6 +328,26 @@ int paresis_cylinder_map(double radius_um, double angle_deg, int dim_x, int dim_
 /* ---------------------------------------------------------------------------------------
  * Small utilities used by the host shim
  * ------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------
+ * Dark-field branch of the ray-tracing model
+ * --------------------------------------------------------------------------------------- */
+
+/* The scattering-angle map of the Lung / 'cylinder_beeds' model (Sample.py:322-343), already in pixels at
+ * the detector (refractionFileNumba2.py:114): df_px = coeff * sqrt(thickness[m]), coeff formed in fp64 on
+ * the host = 2 delta sqrt(NsphereVol^(1/3) * 1e6) sqrt(ln(2/delta) + 1) * z / (pixel * M). */
+int paresis_df_angle(const float* thickness, double coeff, float* df_px, size_t n, paresis_stream stream);
+
+/* refractionFileNumba2.py:130, :143-146: df_clean = df_px with angles above limit_px (Nx/4) dropped;
+ * i_plain = intensity where df_clean == 0 (else 0), i_df = intensity where df_clean != 0 (else 0).
+ * intensity may be NULL (uniform `intensity_uniform`). */
+int paresis_df_split(const float* intensity, float intensity_uniform, const float* df_px, float limit_px,
+                     float* i_plain, float* i_df, float* df_clean, size_t n, paresis_stream stream);
+
+/* refractionFileNumba2.py:171-186: out += for every pixel of `scattered` (the refracted dark-field
+ * intensity) its value spread over a normalised Gaussian patch of sigma = df_px/2 at that pixel
+ * (gaussian_shape, :14-23); df_px == 0 adds the value in place.  out[nx][ny] is accumulated into. */
+int paresis_df_scatter(const float* scattered, const float* df_px, float* out, int nx, int ny, paresis_stream stream);
+
 /* Result transfers (the reference hands back host arrays: Experiment.py:405, :526, main.py:99): an
  * asynchronous device -> pinned-host copy on the library's copy stream, ordered after `producer`.
  * A lane holds the events of one copy in flight; reuse it once paresis_transfer_wait returned. */

@@ -276,12 +276,65 @@ def golden_end_to_end(ref):
         save(name, **out)
 
 
+def golden_darkfield(ref):
+    """The dark-field branch: fastRefractionDF (refractionFileNumba2.py:88-196), setWaveRT with the Lung model
+    (Sample.py:322-343) and one end-to-end position with a scattering sample."""
+    rng = np.random.default_rng(23)
+    r2 = ref["refractionFileNumba2"]
+    shape = (72, 90)
+    pix, z, E, M = 2.9256, 3.6, 52.0, 1.0254
+    x = np.arange(shape[0])[:, None]; y = np.arange(shape[1])[None, :]
+    phi = 40.0 * smooth_field(rng, shape, cells=3)
+    I = 7500.0 * (0.8 + 0.4 * rng.random(shape))
+    blob = np.clip(1.0 - ((x - 36.0) ** 2 + (y - 50.0) ** 2) / 24.0 ** 2, 0.0, None)
+    to_px = z / (pix * 1e-6 * M)
+    out = dict(params=np.array([pix, z, E, M]), I=I, phi=phi)
+    for tag, peak_px in (("narrow", 0.9), ("wide", 2.6)):
+        df = np.sqrt(blob) * peak_px / to_px                     # radians; zero outside the blob
+        if tag == "wide":
+            df[5, 7] = 30.0 / to_px                              # above Nx/4 pixels: dropped at :130
+        res, dx, dy = r2.fastRefractionDF(I.copy(), phi.copy(), z, E, M, pix, df.copy())
+        out["df_" + tag], out["out_" + tag], out["Dx_" + tag] = df, res, dx
+    # setWaveRT with a scattering material
+    S = ref["Sample"].AnalyticalSample
+    smp = object.__new__(S)
+    smp.myMaterials, smp.myType, smp.myName = ["Lung", "PMMA"], "sample_of_interest", "probe"
+    t = np.stack([1.2e-3 * blob, 4e-4 * np.ones(shape)])
+    smp.myGeometry = t
+    smp.delta, smp.beta = [[(E, 2.1e-7)], [(E, 9.9e-8)]], [[(E, 1.3e-10)], [(E, 4.4e-11)]]
+    i_out, phi_out, new_df = smp.setWaveRT(I.copy(), E, phi.copy(), 0)
+    out.update(t=t, sw_I=i_out, sw_phi=phi_out, sw_df=new_df, sw_db=np.array([[2.1e-7, 9.9e-8], [1.3e-10, 4.4e-11]]))
+    save("darkfield", **out)
+
+    # end to end: the bundled experiment with the sphere sample made of Lung
+    e = _experiment(ref, "RayT", "PMMA_sphere", None, None, 1.2, 50.0, (96, 128))
+    e.mySampleofInterest.myMaterials = ["Lung"]
+    # (upstream resolves "Lung" through xraylib's compound parser, absent here: take the coefficients from the
+    # reference's own TablesDeltaBeta.xls, as exported to delta_beta_tables.npz -- the values the shim uses too)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from paresis_b200.hostio import tables
+    energies = [en for en, _ in e.mySource.mySpectrum]
+    db = tables.interpolate("Lung", energies)
+    e.mySampleofInterest.delta = [[(en, float(db[k][0])) for k, en in enumerate(energies)]]
+    e.mySampleofInterest.beta = [[(en, float(db[k][1])) for k, en in enumerate(energies)]]
+    np.random.seed(100)
+    e.myMembrane.myGeometry = []
+    e.myMembrane.getMyGeometry(e.exp_dict["studyDimensions"], e.myMembrane.membranePixelSize, 2, 0, 1)
+    with rh.identity_poisson():
+        res = e.computeSampleAndReferenceImages_RT(0)
+    st = np.array(e.mySampleofInterest.myGeometry)
+    save("e2e_rt_lung", sample=np.asarray(res[0], float), reference=np.asarray(res[1], float), propag=np.asarray(res[2], float),
+         white=np.asarray(res[3], float), df_s4=np.asarray(res[6], float)[::4, ::4], membrane_seed=np.array(100),
+         sample_db=_db(e.mySampleofInterest), sample_t_probe=np.array([st.sum(), st.max()]),
+         mean_energy=np.array(e.exp_dict["meanEnergy"]))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
     only = sys.argv[1:]
     for fn in (golden_splat_kernel, golden_fast_refraction, golden_detector, golden_waves, golden_geometry,
-               golden_end_to_end):
+               golden_end_to_end, golden_darkfield):
         if not only or fn.__name__ in only:
             print(fn.__name__)
             fn(ref)

@@ -178,6 +178,61 @@ def fast_refraction(intensity, phi, distance, energy_kev, magnification, pixel_u
     return out, np.pad(dx, margin), np.pad(dy, margin)
 
 
+def dark_field_angle(thickness_m, delta, model):
+    """Sample.py:322-343: mean scattering angle (rad) of the Lung / 'cylinder_beeds' micro-sphere model and the
+    volume fraction the thickness is scaled by.  ``model`` = "Lung" (alveoli 47 um, fraction 0.5) or
+    "cylinder_beeds" (15 um, 0.6)."""
+    radius, fraction = (47.0, 0.5) if model == "Lung" else (15.0, 0.6)
+    geom = np.asarray(thickness_m, dtype=np.float64) * 1e6
+    n_vol = fraction * 3 / 4 / np.pi / (radius ** 3)
+    n_sphere = n_vol ** (1 / 3) * geom
+    return 2 * delta * n_sphere ** (1 / 2) * np.sqrt(np.log(2 / delta) + 1), fraction
+
+
+def set_wave_rt_df(intensity, phi, thickness, deltas, betas, energy_kev, models):
+    """Sample.py:285-351 WITH the dark-field branch: ``models[m]`` is None, "Lung" or "cylinder_beeds".
+    Returns (I, phi, newDf); newDf is the int 0 when no material scatters (as upstream)."""
+    k = 2 * np.pi * energy_kev * 1000 * 1.6e-19 / (6.626e-34 * 2.998e8)
+    out_i, out_phi, new_df = intensity, phi, 0
+    for t, d, b, model in zip(thickness, deltas, betas, models):
+        geometry = t
+        if model is not None:
+            new_df, fraction = dark_field_angle(t, d, model)
+            geometry = t * fraction
+        out_i = np.exp(-2 * k * b * geometry) * out_i
+        out_phi = out_phi - k * d * geometry
+    return out_i, out_phi, new_df
+
+
+def fast_refraction_df(intensity, phi, distance, energy_kev, magnification, pixel_um, dark_field):
+    """refractionFileNumba2.py:88-196.  Returns (I3[N,N], Dx, Dy) with the displacement maps zero-padded by
+    margin2 = ceil(6 max(DF)) (:116, :126-127, :196)."""
+    nx, ny = np.asarray(intensity).shape
+    df = np.array(dark_field, dtype=np.float64) * distance / (pixel_um * 1e-6 * magnification)      # :114
+    margin2 = int(np.ceil(df.max() * 6))                                                            # :115-117
+    i2, dx, dy = displacement(intensity, phi, distance, energy_kev, magnification, pixel_um)       # :120-129
+    df[df > nx / 4] = 0                                                                             # :130
+    plain = np.where(df != 0, 0.0, i2)                                                              # :143-146
+    scat = np.where(df == 0, 0.0, i2)
+    out = splat(plain, dx, dy, margin2)                                                             # :154
+    moved = splat(scat, dx, dy, margin2)                                                            # :155
+    for i in range(nx):                                                                             # :171-186
+        for j in range(ny):
+            v = moved[i, j]
+            if v == 0:
+                continue
+            if df[i, j] != 0:
+                patch = gaussian_kernel(df[i, j] / 2)
+                h = patch.shape[0] // 2
+                r0, r1, c0, c1 = max(i - h, 0), min(i + h + 1, nx), max(j - h, 0), min(j + h + 1, ny)   # cropped at :189
+                out[r0:r1, c0:c1] += v * patch[r0 - i + h:r1 - i + h, c0 - j + h:c1 - j + h]
+            else:
+                out[i, j] += v
+    if np.isnan(out).any() or np.any(np.abs(out) > 1e50):
+        raise InsaneValues("The calculated intensity refractive includes some nans or insane values")
+    return out, np.pad(dx, margin2), np.pad(dy, margin2)
+
+
 def bin_sum(image, size_x, size_y):
     """Detector.py:185-198 (resize)."""
     img = _c64(image)

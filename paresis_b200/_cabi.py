@@ -27,6 +27,7 @@ EXPORTS = (
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
+    "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
     "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
@@ -129,6 +130,9 @@ def _load():
         "paresis_mean": [vp, sz, vp, vp],
         "paresis_sum_scaled": [vp, sz, cd, vp, vp],
         "paresis_rt_run": [ctypes.POINTER(RtJob), vp],
+        "paresis_df_angle": [vp, cd, vp, sz, vp],
+        "paresis_df_split": [vp, cf, vp, cf, vp, vp, vp, sz, vp],
+        "paresis_df_scatter": [vp, vp, vp, ci, ci, vp],
         "paresis_transfer_lane_create": [ctypes.POINTER(vp)],
         "paresis_transfer_lane_destroy": [vp],
         "paresis_transfer_d2h": [vp, vp, vp, sz, vp],
@@ -449,6 +453,26 @@ def membrane_from_field(field, offsets, margin, dim_x, dim_y, out):
     _check(_timed("raster_spheres", lambda: lib.paresis_membrane_from_field(
         _ptr(field, torch.float32), fx, fy, offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), offs.shape[0], margin,
         dim_x, dim_y, _ptr(out, torch.float32), _stream())), "paresis_membrane_from_field")
+    _count()
+
+
+def df_angle(thickness, coeff, df_px):
+    _check(lib.paresis_df_angle(_ptr(thickness, torch.float32), float(coeff), _ptr(df_px, torch.float32), thickness.numel(),
+                                _stream()), "paresis_df_angle")
+    _count()
+
+
+def df_split(intensity, intensity_uniform, df_px, limit_px, i_plain, i_df, df_clean):
+    _check(lib.paresis_df_split(_ptr(intensity, torch.float32), float(intensity_uniform), _ptr(df_px, torch.float32),
+                                float(limit_px), _ptr(i_plain, torch.float32), _ptr(i_df, torch.float32),
+                                _ptr(df_clean, torch.float32), df_px.numel(), _stream()), "paresis_df_split")
+    _count()
+
+
+def df_scatter(scattered, df_px, out):
+    nx, ny = out.shape
+    _check(lib.paresis_df_scatter(_ptr(scattered, torch.float32), _ptr(df_px, torch.float32), _ptr(out, torch.float32), nx, ny,
+                                  _stream()), "paresis_df_scatter")
     _count()
 
 

@@ -198,3 +198,45 @@ def test_positions_in_one_call_match_one_by_one(shim, name):
         assert out["firsts"] == [0]
         assert rel_l2(out["propag"][0].cpu().numpy(), single[0][1][2]) < 1e-6
         assert rel_l2(out["white"][0].cpu().numpy(), single[0][1][3]) < 1e-6
+
+
+def test_dark_field_branch(shim, golden):
+    """fastRefractionDF / refraction(..., darkField) / setWaveRT with the Lung model, and one end-to-end
+    position with a scattering sample, against the unmodified reference."""
+    r2 = importlib.import_module("refractionFileNumba2")
+    g = golden("darkfield")
+    pix, z, E, M = g["params"]
+    for tag in ("narrow", "wide"):
+        out, dx, dy = r2.fastRefractionDF(g["I"].copy(), g["phi"], z, E, M, pix, g["df_" + tag])
+        assert out.dtype == np.float64 and dx.shape == g["Dx_" + tag].shape
+        assert rel_l2(dx, g["Dx_" + tag]) < 1e-6
+        assert rel_l2(out, g["out_" + tag]) < TOL, tag
+    Sample = importlib.import_module("Sample")
+    s = Sample.AnalyticalSample()
+    s.myType, s.myName, s.myMaterials = "sample_of_interest", "probe", ["Lung", "PMMA"]
+    s.delta = [[(E, g["sw_db"][0][0])], [(E, g["sw_db"][0][1])]]
+    s.beta = [[(E, g["sw_db"][1][0])], [(E, g["sw_db"][1][1])]]
+    s.myGeometry = g["t"]
+    i_out, phi_out, df = s.setWaveRT(g["I"], E, g["phi"])
+    assert rel_l2(i_out, g["sw_I"]) < 1e-6 and rel_l2(phi_out, g["sw_phi"]) < 1e-6 and rel_l2(df, g["sw_df"]) < 1e-6
+    # end to end: the sphere sample made of Lung
+    ge = golden("e2e_rt_lung")
+    d = dict(experimentName="Small_sphere_mono", filepath="unused/", overSampling=2, nbExpPoints=1, simulation_type="RayT",
+             expID="t", poissonNoise=False)
+    e = shim.Experiment(d)
+    smp = e.mySampleofInterest
+    smp.myMaterials = ["Lung"]
+    smp.delta, smp.beta = [], []
+    smp.getDeltaBeta(e.mySource.mySpectrum)
+    assert np.allclose([v for _, v in smp.delta[0]], ge["sample_db"][:, 1], rtol=1e-12)
+    np.random.seed(int(ge["membrane_seed"]))
+    e.myMembrane.myGeometry = []
+    e.myMembrane.getMyGeometry(e.exp_dict['studyDimensions'], e.myMembrane.membranePixelSize, 2, 0, 1)
+    res = e.computeSampleAndReferenceImages_RT(0)
+    assert len(res) == 7
+    for k, name in enumerate(("sample", "reference", "propag", "white")):
+        assert rel_l2(res[k], ge[name]) < TOL, name
+    assert rel_l2(res[6][::4, ::4], ge["df_s4"]) < 1e-6
+    assert abs(e.exp_dict["meanEnergy"] / float(ge["mean_energy"]) - 1) < 1e-5
+    # the sample image really differs from a non-scattering one
+    assert rel_l2(res[0], ge["reference"]) > 1e-3

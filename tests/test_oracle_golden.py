@@ -176,3 +176,16 @@ def test_end_to_end(golden, name):
             assert rel_l2(white, g["white_p0"]) < tol
         else:
             assert not propag.any()
+
+
+def test_dark_field_branch(golden):
+    """fastRefractionDF (refractionFileNumba2.py:88-196) and setWaveRT with the Lung model (Sample.py:322-343)."""
+    g = golden("darkfield")
+    pix, z, E, M = g["params"]
+    for tag in ("narrow", "wide"):
+        out, dx, dy = po.fast_refraction_df(g["I"].copy(), g["phi"], z, E, M, pix, g["df_" + tag])
+        assert dx.shape == g["Dx_" + tag].shape
+        assert rel_l2(dx, g["Dx_" + tag]) < 1e-12
+        assert rel_l2(out, g["out_" + tag]) < 1e-12, tag
+    i_out, phi_out, df = po.set_wave_rt_df(g["I"], g["phi"], g["t"], g["sw_db"][0], g["sw_db"][1], E, ["Lung", None])
+    assert rel_l2(i_out, g["sw_I"]) < 1e-13 and rel_l2(phi_out, g["sw_phi"]) < 1e-13 and rel_l2(df, g["sw_df"]) < 1e-13
