@@ -135,30 +135,28 @@ raster_gather_kernel(const int* __restrict__ n_caps_all, const Cap* __restrict__
 // One membrane position from the once-rasterised sphere field: the grain map is translation
 // invariant (getMembraneFromFile.py:139-161 only shifts the list by integer pixels per layer), so
 // out[r][c] = sum over layers of field[ox_l + margin + r][oy_l + margin + c].
-// A thread owns four consecutive columns; window starts are arbitrary, so loads are scalar (coalesced).
+// Window starts are arbitrary, so loads are scalar; a thread owns four columns 256 apart, which keeps every
+// load and store instruction of a warp on 32 consecutive floats.
 __global__ void __launch_bounds__(256)
 membrane_from_field_kernel(const float* __restrict__ field, int field_x, int field_y, LayerOffsets off, int n_layers, int margin,
                            int dim_x, int dim_y, float* __restrict__ out) {
-    const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int c0 = blockIdx.x * 1024 + threadIdx.x;
     const int r = blockIdx.y;
-    if (c >= dim_y) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int l = 0; l < n_layers; ++l) {
-        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c;
+        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c0;
         if (fr < 0 || fr >= field_x) continue;
         const float* src = field + (size_t)fr * field_y;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (fc + k >= 0 && fc + k < field_y) acc[k] += __ldg(src + fc + k);
+        for (int k = 0; k < 4; ++k) {
+            const long long f = fc + 256 * k;
+            if (c0 + 256 * k < dim_y && f >= 0 && f < field_y) acc[k] += __ldg(src + f);
+        }
     }
-    float* o = out + (size_t)r * dim_y + c;
-    if (c + 3 < dim_y && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    } else {
+    float* o = out + (size_t)r * dim_y + c0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (c + k < dim_y) o[k] = acc[k];
-    }
+    for (int k = 0; k < 4; ++k)
+        if (c0 + 256 * k < dim_y) o[256 * k] = acc[k];
 }
 
 __global__ void sphere_map_kernel(double rad, double scale_m, int dim_x, int dim_y, float* __restrict__ out) {
