@@ -41,9 +41,7 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
     if (by) dy = 0.f;
 }
 
-// Shared-memory tile variant (refract_tile.cu): config 0 = 16 rows / halo 4, 1 = 32 rows / halo 8.
-int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, int config, cudaStream_t s);
-// Two-columns-per-thread variant (refract_pair.cu); needs an even pitch and 8-byte aligned images.
-int dispatch_refract_pair(int n_layers, const RefractArgs<float>& a, int rows_override, cudaStream_t s);
+// Fixed-point shared-memory tile kernel (refract_tile.cu): tiles of up to 16 source rows x 256 columns, halo 4.
+int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 
 }  // namespace paresis

@@ -23,9 +23,8 @@ static int dispatch_tile_layers(int n_layers, const RefractArgs<float>& a, cudaS
     }
 }
 
-int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, int config, cudaStream_t s) {
-    if (config == 3) return dispatch_tile_layers<8, 8>(n_layers, a, s);
-    return config == 1 ? dispatch_tile_layers<16, 8>(n_layers, a, s) : dispatch_tile_layers<16, 4>(n_layers, a, s);
+int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_t s) {
+    return dispatch_tile_layers<16, 4>(n_layers, a, s);
 }
 
 }  // namespace paresis
