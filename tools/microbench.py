@@ -118,21 +118,13 @@ def main():
         ibs = torch.zeros((n, n), device=dev)
         o1 = torch.zeros((n, n), device=dev); o2 = torch.zeros((n, n), device=dev)
         layers = [(t_mem, 5.97e-7 * s3, 5.97e-7 * s3, 0.0), (t_smp, 9.85e-8 * s3, 0.0, 2 * k * 3.16e-12)]
-        for mode in (0, 2):
-            abi.set_tuning(0, mode)
-            for rows in (0, 8, 16, 32):
-                abi.set_tuning(1, rows)
-                med, best = timeit(lambda: abi.refract_layers(None, 7500.0, [(t_mem, 5.97e-7 * s2, 0.0, 2 * k * 5.37e-9)], ibs), flush=flush)
-                rec("refract_membrane_hop", n, med, best, 8 * px, mode=mode, rows=rows)
-                med, best = timeit(lambda: abi.refract_layers(ibs, 0.0, layers, o1, o2), flush=flush)
-                rec("refract_sample_ref_hop", n, med, best, 20 * px, mode=mode, rows=rows)
-        abi.set_tuning(0, 2); abi.set_tuning(1, 0)
-        # the same hop with its outputs warm in L2 (zero-filled just before, as the pipeline does)
-        def hop_warm():
-            o1.zero_(); o2.zero_()
-            abi.refract_layers(ibs, 0.0, layers, o1, o2)
-        med, best = timeit(hop_warm, flush=flush)
-        rec("memset2+refract_sample_ref_hop", n, med, best, 20 * px)
+        # hop kernels: the fp32 direct-to-L2 kernel (no intensity scale) and the fixed-point tile kernel (production)
+        for label, scale in (("direct", 0.0), ("tile", 7500.0)):
+            med, best = timeit(lambda: abi.refract_layers(None, 7500.0, [(t_mem, 5.97e-7 * s2, 0.0, 2 * k * 5.37e-9)], ibs,
+                                                          intensity_scale=scale), flush=flush)
+            rec("refract_membrane_hop", n, med, best, 8 * px, variant=label)
+            med, best = timeit(lambda: abi.refract_layers(ibs, 0.0, layers, o1, o2, intensity_scale=scale), flush=flush)
+            rec("refract_sample_ref_hop", n, med, best, 20 * px, variant=label)
         det = n // 2
         work = torch.empty(abi.detect_work_floats(n, n, 2, det, det), device=dev)
         expect = torch.empty((det, det), device=dev)
@@ -144,6 +136,9 @@ def main():
         rec("detect_fused_nonoise", n, med, best, 4 * px + 4 * det * det)
         med, best = timeit(lambda: abi.detect_counts(o1, 2, det, det, src, psf, work, expect, True, 1, 2), flush=flush)
         rec("detect_fused_poisson", n, med, best, 4 * px + 4 * det * det)
+        e2 = torch.empty((det, det), device=dev)
+        med, best = timeit(lambda: abi.detect_counts_multi([o1, o2], 2, det, det, src, psf, work, [expect, e2], True, 1, [2, 3]), flush=flush)
+        rec("detect_two_images_poisson", n, med, best, 2 * (4 * px + 4 * det * det))
         counts = torch.empty((det, det), device=dev)
         med, best = timeit(lambda: abi.poisson(expect, counts, 1, 2), flush=flush)
         rec("poisson", n, med, best, 8 * det * det)
