@@ -251,8 +251,9 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
         }
     }
     if (noise) {
-        // Finish the queued draws in rounds: round t runs PTRS trial t for every pixel still open and
-        // re-queues the rejected ones (~12 %), so warps stay dense instead of looping on their slowest lane.
+        // Finish the queued draws in rounds (poisson_round: the full test of the candidate the quick test left
+        // open, then two fresh candidates per round); the few pixels still open are re-queued, so warps stay
+        // dense instead of looping on their slowest lane.
         int2* qcur = queue;
         int2* qnext = reinterpret_cast<int2*>(R1);     // R3 (= R1) is dead after phase 4
         int* ncur = &n_queued;
@@ -267,7 +268,7 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
                 const int2 e = qcur[qi];
                 const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
                 float x;
-                if (poisson_trial(__int_as_float(e.y), seed, seq, p, trial, x)) out[p] = x;
+                if (poisson_round(__int_as_float(e.y), seed, seq, p, trial, x)) out[p] = x;
                 else qnext[atomicAdd(nnext, 1)] = e;
             }
             int2* tq = qcur; qcur = qnext; qnext = tq;

@@ -133,32 +133,8 @@ __device__ __forceinline__ void poisson_quick2(float lam0, float lam1, uint64_t 
     ok1 = poisson_decide(lam1, r[2], r[3], x1);
 }
 
-// One PTRS trial (or the whole draw when the mean is small) of pixel `pixel`: returns true and the
-// variate when the draw is decided.  Trial t uses Philox block (pair, t); trial 0 replays the words the
-// quick test saw, so poisson_quick + poisson_trial(0, 1, ...) is one consistent stream.
-//   lam <= 0 -> 0;  lam < 10 -> inversion by sequential search (decided at trial 0);  else PTRS.
-static __device__ __noinline__ bool poisson_trial(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t trial,
-                                                  float& result) {
-    if (!(lam > 0.f)) { result = 0.f; return true; }
-    Philox g = poisson_stream(seed, seq, pixel);
-    g.c[1] = trial;
-    uint32_t r[4];
-    g.generate(r);
-    const bool hi = pixel & 1;
-    const uint32_t ra = hi ? r[2] : r[0], rb = hi ? r[3] : r[1];
-    if (lam < 10.f) {
-        const float u = (float)u01d(ra, rb);
-        float p = expf(-lam), F = p;
-        int x = 0;
-        while (u > F && x < 200) {
-            ++x;
-            p *= lam / (float)x;
-            F += p;
-        }
-        result = (float)x;
-        return true;
-    }
-    const PtrsSetup t(lam);
+// The full PTRS test of one candidate (U, V from two random words): true = accepted, k in `result`.
+__device__ __forceinline__ bool ptrs_trial(const PtrsSetup& t, float lam, float log_invalpha, uint32_t ra, uint32_t rb, float& result) {
     const float U = u01f(ra) - 0.5f, V = u01f(rb);
     const float us = 0.5f - fabsf(U);
     const float k = t.candidate(lam, U, us);
@@ -166,16 +142,63 @@ static __device__ __noinline__ bool poisson_trial(float lam, uint64_t seed, uint
     if (us >= 0.07f && V <= t.vr) return true;
     if (k < 0.f || (us < 0.013f && V > us)) return false;
     // lg2-based logs (abs. error ~1e-6) on the hat side; the pmf side is the accurate one
-    const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
     return __logf(V) + log_invalpha - __logf(fmaf(t.a, rcp_fast(us * us), t.b)) <= log_poisson_pmf(k, lam);
+}
+
+// Everything the quick test leaves open, in ROUNDS so that the detector kernel can keep its warps dense:
+//   round 0 : replays the pair block of the quick test (same two words) -- lam <= 0 -> 0, lam < 10 -> inversion
+//             by sequential search, else the full PTRS test of trial 0; if that fails, rounds continue with
+//   round r : Philox block (pixel, r | 2^31) = TWO more candidates per block (words 0,1 then 2,3).
+// Returns true and the variate once the draw is decided.  A draw is still a pure function of
+// (seed, sequence, pixel): poisson_draw() below walks the same rounds.
+static __device__ __noinline__ bool poisson_round(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t round,
+                                                  float& result) {
+    if (!(lam > 0.f)) { result = 0.f; return true; }
+    uint32_t r[4];
+    if (round == 0) {
+        Philox g = poisson_stream(seed, seq, pixel);
+        g.generate(r);
+        const bool hi = pixel & 1;
+        const uint32_t ra = hi ? r[2] : r[0], rb = hi ? r[3] : r[1];
+        if (lam < 10.f) {
+            const float u = (float)u01d(ra, rb);
+            float p = expf(-lam), F = p;
+            int x = 0;
+            while (u > F && x < 200) {
+                ++x;
+                p *= lam / (float)x;
+                F += p;
+            }
+            result = (float)x;
+            return true;
+        }
+        const PtrsSetup t(lam);
+        const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
+        if (ptrs_trial(t, lam, log_invalpha, ra, rb, result)) return true;
+        round = 1;      // ~82 % of the queued candidates are rejected: go on with this pixel's own block right away
+    } else {
+        ++round;        // caller's round r >= 1 is block r + 1 (block 1 was consumed inside round 0)
+    }
+    const PtrsSetup t(lam);
+    const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
+    Philox g;
+    g.c[0] = (uint32_t)pixel;
+    g.c[1] = round | 0x80000000u;
+    g.c[2] = (uint32_t)seq;
+    g.c[3] = (uint32_t)(seq >> 32) ^ (uint32_t)(pixel >> 32);
+    g.k[0] = (uint32_t)seed;
+    g.k[1] = (uint32_t)(seed >> 32);
+    g.generate(r);
+    if (ptrs_trial(t, lam, log_invalpha, r[0], r[1], result)) return true;
+    return ptrs_trial(t, lam, log_invalpha, r[2], r[3], result);
 }
 
 // The complete draw.
 static __device__ float poisson_slow(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
     float x;
-    for (uint32_t trial = 0; trial < 64; ++trial)
-        if (poisson_trial(lam, seed, seq, pixel, trial, x)) return x;
-    return floorf(lam + 0.5f);  // unreachable in practice (acceptance > 0.88 per trial)
+    for (uint32_t round = 0; round < 32; ++round)
+        if (poisson_round(lam, seed, seq, pixel, round, x)) return x;
+    return floorf(lam + 0.5f);  // unreachable in practice (two candidates per round, acceptance > 0.88 each)
 }
 
 __device__ __forceinline__ float poisson_draw(float lam, uint64_t seed, uint64_t seq, uint64_t pixel) {
