@@ -75,9 +75,11 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
                 PARESIS_CUDA(cudaMemsetAsync(job->dx_pad, 0, sizeof(float) * np, s));
                 PARESIS_CUDA(cudaMemsetAsync(job->dy_pad, 0, sizeof(float) * np, s));
             }
-            rc = paresis_refract_layers(nullptr, en.intensity_propag, en.propag, en.n_propag, job->acc_propag, nullptr,
-                                        want_d ? job->dx_pad : nullptr, want_d ? job->dy_pad : nullptr, job->nx, job->ny,
-                                        margin, job->flag, stream);
+            paresis_refract_extras x3{};
+            x3.intensity_scale = en.intensity_propag;
+            rc = paresis_refract_layers_ex(nullptr, en.intensity_propag, en.propag, en.n_propag, job->acc_propag, nullptr,
+                                           want_d ? job->dx_pad : nullptr, want_d ? job->dy_pad : nullptr, job->nx, job->ny,
+                                           margin, job->flag, &x3, stream);
             if (rc) return rc;
             white += en.intensity_propag;
         }
