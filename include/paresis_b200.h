@@ -325,6 +325,11 @@ int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, fl
 int paresis_cylinder_map(double radius_um, double angle_deg, int dim_x, int dim_y, double pix_um,
                          float* out, paresis_stream stream);
 
+/* CreateSampleSpheresInCylinder (kind 0) / CreateSampleSpheresInParallelepiped (kind 1) --
+ * Samples/createSampGeom.py:110-260: two 500 um spheres (materials 0, 1) in a vertical tube (material 2 =
+ * tube - spheres; kind 1 is rotated by 15 degrees like imutils.rotate).  out3[3][dim_x][dim_y], metres. */
+int paresis_two_sphere_phantom(int kind, int dim_x, int dim_y, double pix_um, float* out3, paresis_stream stream);
+
 /* ---------------------------------------------------------------------------------------
  * Small utilities used by the host shim
  * ------------------------------------------------------------------------------------- */

@@ -329,12 +329,26 @@ def golden_darkfield(ref):
          mean_energy=np.array(e.exp_dict["meanEnergy"]))
 
 
+def golden_phantoms(ref):
+    """CreateSampleSpheresInCylinder / CreateSampleSpheresInParallelepiped (createSampGeom.py:110-260)."""
+    geom = ref["geom"]
+    out = {}
+    for tag, fn, dx, dy, pix in (("cyl_a", geom.CreateSampleSpheresInCylinder, 420, 300, 10.0),
+                                 ("cyl_b", geom.CreateSampleSpheresInCylinder, 500, 260, 8.3),
+                                 ("par_a", geom.CreateSampleSpheresInParallelepiped, 300, 300, 12.0),
+                                 ("par_b", geom.CreateSampleSpheresInParallelepiped, 260, 340, 9.7)):
+        g, params = fn("x", dx, dy, pix)
+        out[tag] = np.asarray(g, dtype=np.float64)
+        out[tag + "_cfg"] = np.array([dx, dy, pix])
+    save("phantoms", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
     only = sys.argv[1:]
     for fn in (golden_splat_kernel, golden_fast_refraction, golden_detector, golden_waves, golden_geometry,
-               golden_end_to_end, golden_darkfield):
+               golden_end_to_end, golden_darkfield, golden_phantoms):
         if not only or fn.__name__ in only:
             print(fn.__name__)
             fn(ref)

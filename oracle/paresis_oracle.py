@@ -426,6 +426,50 @@ def sample_cylinder(radius_um, orientation_deg, dim_x, dim_y, pix):
     return rot[None, dx0:dx0 + dim_x, dy0:dy0 + dim_y] * pix * 1e-6
 
 
+def sample_two_spheres(kind, dim_x0, dim_y0, pix):
+    """Samples/createSampGeom.py:110-172 (kind 0, spheres in a cylinder) and :174-260 (kind 1, spheres in a rounded
+    parallelepiped on a canvas with margin max(dim)//2, rotated by 15 degrees, cropped).  [3, dimX, dimY] metres."""
+    r0 = 500.0
+    margin = 0 if kind == 0 else max(dim_x0, dim_y0) // 2
+    dim_x, dim_y = dim_x0 + 2 * margin, dim_y0 + 2 * margin
+    rad = r0 / pix
+    ps2 = int(np.ceil(rad))
+    ps = 2 * ps2
+    if 2 * rad > dim_x or 2 * rad > dim_y:
+        raise Exception("The sample is too big for the detector field of view (increase dimX, dimY)")
+    i = np.arange(ps, dtype=np.float64)
+    dist = (ps / 2 - i[:, None]) ** 2 + (ps / 2 - i[None, :]) ** 2
+    patch = np.where(dist < rad ** 2, 2 * np.sqrt(np.maximum(rad ** 2 - (ps / 2 - i[None, :]) ** 2 - (ps / 2 - i[:, None]) ** 2, 0.0)), 0.0)
+    rt = 2 * r0 / pix
+    if 2 * rt > dim_x or 2 * rt > dim_y:
+        raise Exception("The sample is too big for the detector field of view (increase dimX, dimY)")
+    tube = np.zeros((dim_x, dim_y))
+    if kind == 0:
+        pos_y = dim_y // 2
+        pos_a, pos_b = int(np.round(r0 * 3 / pix)), int(np.round(r0 * 7 / pix))
+        j = np.arange(dim_y, dtype=np.float64)
+        tube[:, :] = np.where(np.abs(dim_y / 2 - j) < rt, 2 * np.sqrt(np.maximum(rt ** 2 - (dim_y / 2 - j) ** 2, 0.0)), 0.0)[None, :]
+    else:
+        pos_y = dim_y // 2
+        pos_a, pos_b = dim_x * 2 // 5, dim_x * 3 // 5
+        for j in range(dim_x):                                               # :222 (sic: columns, bounded by dimX)
+            if abs(dim_y / 2 - j) < rt * 3 / 4:
+                tube[:, j] = rt * 2
+            if rt > (j - dim_y / 2) >= rt * 3 / 4:
+                tube[:, j] = rt / 2 * 3 + 2 * np.sqrt((rt / 4) ** 2 - (j - (dim_y / 2 + rt * 3 / 4)) ** 2)
+            if -rt < j - dim_y / 2 <= -rt * 3 / 4:
+                tube[:, j] = rt / 2 * 3 + 2 * np.sqrt((rt / 4) ** 2 - (j - (dim_y / 2 - rt * 3 / 4)) ** 2)
+    out = np.zeros((3, dim_x, dim_y))
+    out[0, pos_a - ps2:pos_a + ps2, pos_y - ps2:pos_y + ps2] = patch
+    out[1, pos_b - ps2:pos_b + ps2, pos_y - ps2:pos_y + ps2] = patch
+    out[2] = tube - out[0] - out[1]
+    if kind == 1:
+        mat = rotation_matrix((dim_y // 2, dim_x // 2), 15)
+        out = np.stack([warp_affine_linear(out[m], mat, dim_y, dim_x) for m in range(3)])
+        out = out[:, margin:dim_x - margin, margin:dim_y - margin]
+    return out * pix * 1e-6
+
+
 # --------------------------------------------------------------------------- orchestration
 class Setup:
     """The scalars the per-energy loop needs (what Experiment.__init__ derives from the XML,

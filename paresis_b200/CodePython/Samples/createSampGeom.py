@@ -1,8 +1,7 @@
 """Sample thickness maps -- drop-in for Samples/createSampGeom.py.
 
-Sphere and cylinder (the bundled configurations) are rendered by CUDA kernels; image-stack and
-template geometries are host-side conveniences.  The two multi-sphere demo phantoms
-(createSampGeom.py:110-260) are not part of the accelerated path.
+Sphere, cylinder and the two multi-sphere phantoms are rendered by CUDA kernels; image-stack and
+template geometries are host-side conveniences.
 """
 import glob
 
@@ -59,16 +58,25 @@ def CreateYourSampleGeometry(myName, dimX0, dimY0, pixelSize):
                                                     'geometry other parameter': ("unitlessParameter", '')}
 
 
-def _not_accelerated(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError("%s is a fixed demo phantom outside the accelerated hot path (SURVEY.md section 2, #9); "
-                                  "render it once with PARESIS and load it with loadSampleGeometryFromImages" % name)
-    fn.__name__ = name
-    return fn
+def CreateSampleSpheresInCylinder(myName, dimX, dimY, pixelSize):
+    """Two 500 um spheres in a vertical cylinder, three materials (createSampGeom.py:110-172)."""
+    r0 = 500
+    geom = geometry.sample_two_spheres(0, dimX, dimY, pixelSize)
+    pos1, pos2 = int(np.round(r0 * 3 / pixelSize)), int(np.round(r0 * 7 / pixelSize))
+    return geom, {'Spheres_radius': (r0, 'um'), 'Cylinder_radius': (r0 * 2, 'um'),
+                  'Position_Sphere_1': (pos1 * pixelSize, 'um'), 'Position_Sphere_2': (pos2 * pixelSize, 'um')}
 
 
-CreateSampleSpheresInCylinder = _not_accelerated("CreateSampleSpheresInCylinder")
-CreateSampleSpheresInParallelepiped = _not_accelerated("CreateSampleSpheresInParallelepiped")
+def CreateSampleSpheresInParallelepiped(myName, dimX0, dimY0, pixelSize):
+    """Two 500 um spheres in a tilted, rounded parallelepiped, three materials (createSampGeom.py:174-260)."""
+    r0 = 500
+    margin = max(dimX0, dimY0) // 2
+    dim_x = dimX0 + 2 * margin
+    if abs(dim_x * 3 // 5 - dim_x * 2 // 5) < r0 / pixelSize * 2:
+        print("/!\\ sample spheres overlapping!")
+    geom = geometry.sample_two_spheres(1, dimX0, dimY0, pixelSize)
+    return geom, {'Spheres_radius': (r0, 'um'), 'Parallelepipede_size': (r0 * 2, 'um'),
+                  'Position_Sphere_1': (dim_x * 2 // 5 * pixelSize, 'um'), 'Position_Sphere_2': (dim_x * 3 // 5 * pixelSize, 'um')}
 
 
 def getText(node):

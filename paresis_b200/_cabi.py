@@ -27,7 +27,7 @@ EXPORTS = (
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
-    "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
+    "paresis_two_sphere_phantom", "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
     "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
@@ -130,6 +130,7 @@ def _load():
         "paresis_mean": [vp, sz, vp, vp],
         "paresis_sum_scaled": [vp, sz, cd, vp, vp],
         "paresis_rt_run": [ctypes.POINTER(RtJob), vp],
+        "paresis_two_sphere_phantom": [ci, ci, ci, cd, vp, vp],
         "paresis_df_angle": [vp, cd, vp, sz, vp],
         "paresis_df_split": [vp, cf, vp, cf, vp, vp, vp, sz, vp],
         "paresis_df_scatter": [vp, vp, vp, ci, ci, vp],
@@ -453,6 +454,12 @@ def membrane_from_field(field, offsets, margin, dim_x, dim_y, out):
     _check(_timed("raster_spheres", lambda: lib.paresis_membrane_from_field(
         _ptr(field, torch.float32), fx, fy, offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), offs.shape[0], margin,
         dim_x, dim_y, _ptr(out, torch.float32), _stream())), "paresis_membrane_from_field")
+    _count()
+
+
+def two_sphere_phantom(kind, dim_x, dim_y, pix_um, out3):
+    _check(lib.paresis_two_sphere_phantom(int(kind), dim_x, dim_y, float(pix_um), _ptr(out3, torch.float32), _stream()),
+           "paresis_two_sphere_phantom")
     _count()
 
 

@@ -202,6 +202,74 @@ __global__ void cylinder_map_kernel(Affine inv, double rad, double scale_m, int 
     out[(size_t)i * dim_y + j] = (float)(v * scale_m);
 }
 
+// The two demo phantoms of createSampGeom.py:110-260: two spheres (materials 0 and 1) inside a vertical
+// tube (material 2 = tube - spheres); kind 0 = cylinder on the study grid, kind 1 = rounded parallelepiped
+// built on a canvas with a margin of max(dim)/2, rotated by 15 degrees (imutils.rotate = cv2.warpAffine,
+// same fixed-point taps as cylinder_map_kernel) and cropped.  Evaluated analytically: no canvas in memory.
+struct Phantom {
+    int kind, nxp, nyp;          // canvas
+    int pos_x0, pos_x1, pos_y;   // sphere centres
+    int ps2;                     // half patch size, ceil(r)
+    double r_sphere, r_tube;     // pixels
+};
+
+__device__ __forceinline__ double phantom_sphere(const Phantom& ph, long long row, long long col, int pos_x) {
+    const long long i = row - (pos_x - ph.ps2), j = col - (ph.pos_y - ph.ps2);      // patch coordinates (:149-150, :236-237)
+    if (i < 0 || i >= 2 * ph.ps2 || j < 0 || j >= 2 * ph.ps2) return 0.0;
+    const double di = (double)ph.ps2 - (double)i, dj = (double)ph.ps2 - (double)j;
+    const double dist = di * di + dj * dj;
+    return dist < ph.r_sphere * ph.r_sphere ? 2.0 * sqrt(ph.r_sphere * ph.r_sphere - dj * dj - di * di) : 0.0;
+}
+
+__device__ __forceinline__ double phantom_tube(const Phantom& ph, long long col) {
+    const double r = ph.r_tube, c = ph.nyp / 2.0;
+    if (ph.kind == 0) {                                                      // :141-143
+        const double d = c - (double)col;
+        return fabs(d) < r ? 2.0 * sqrt(r * r - d * d) : 0.0;
+    }
+    if (col >= ph.nxp) return 0.0;                                           // `for j in range(dimX)` (:222)
+    double t = 0.0;                                                          // :223-228, later tests overwrite earlier ones
+    const double j = (double)col;
+    if (fabs(c - j) < r * 3 / 4) t = r * 2;
+    if (r > (j - c) && (j - c) >= r * 3 / 4) { const double e = j - (c + r * 3 / 4); t = r / 2 * 3 + 2.0 * sqrt((r / 4) * (r / 4) - e * e); }
+    if (-r < (j - c) && (j - c) <= -r * 3 / 4) { const double e = j - (c - r * 3 / 4); t = r / 2 * 3 + 2.0 * sqrt((r / 4) * (r / 4) - e * e); }
+    return t;
+}
+
+__device__ __forceinline__ void phantom_at(const Phantom& ph, long long col, long long row, double v[3]) {
+    v[0] = v[1] = v[2] = 0.0;
+    if (col < 0 || col >= ph.nyp || row < 0 || row >= ph.nxp) return;      // BORDER_CONSTANT
+    v[0] = phantom_sphere(ph, row, col, ph.pos_x0);
+    v[1] = phantom_sphere(ph, row, col, ph.pos_x1);
+    v[2] = phantom_tube(ph, col) - v[0] - v[1];
+}
+
+__global__ void phantom_kernel(Phantom ph, Affine inv, int rotate, int row0, int col0, double scale_m, int dim_x, int dim_y,
+                               float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= dim_y) return;
+    const int row = i + row0, col = j + col0;
+    double acc[3];
+    if (!rotate) {
+        phantom_at(ph, col, row, acc);
+    } else {
+        const long long adelta = __double2ll_rn(inv.m[0] * col * 1024.0);
+        const long long bdelta = __double2ll_rn(inv.m[3] * col * 1024.0);
+        const long long x0 = __double2ll_rn((inv.m[1] * row + inv.m[2]) * 1024.0) + 16;
+        const long long y0 = __double2ll_rn((inv.m[4] * row + inv.m[5]) * 1024.0) + 16;
+        const long long X = (x0 + adelta) >> 5, Y = (y0 + bdelta) >> 5;
+        const long long sx = X >> 5, sy = Y >> 5;
+        const double fx = (double)(X & 31) / 32.0, fy = (double)(Y & 31) / 32.0;
+        double a[3], b[3], c[3], d[3];
+        phantom_at(ph, sx, sy, a); phantom_at(ph, sx + 1, sy, b); phantom_at(ph, sx, sy + 1, c); phantom_at(ph, sx + 1, sy + 1, d);
+        for (int m = 0; m < 3; ++m)
+            acc[m] = a[m] * ((1.0 - fx) * (1.0 - fy)) + b[m] * (fx * (1.0 - fy)) + c[m] * ((1.0 - fx) * fy) + d[m] * (fx * fy);
+    }
+    const size_t n = (size_t)dim_x * dim_y, p = (size_t)i * dim_y + j;
+    for (int m = 0; m < 3; ++m) out[m * n + p] = (float)(acc[m] * scale_m);
+}
+
 }  // namespace paresis
 
 using namespace paresis;
@@ -281,6 +349,68 @@ extern "C" int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double
     if (!out || dim_x < 1 || dim_y < 1 || !(pix_um > 0)) { set_last_error("paresis_sphere_map: bad arguments"); return PARESIS_ERR_ARG; }
     sphere_map_kernel<<<dim3(div_up(dim_y, 128), dim_x), 128, 0, (cudaStream_t)stream>>>(radius_um / pix_um, pix_um * 1e-6, dim_x, dim_y, out);
     PARESIS_LAUNCH_CHECK("sphere_map_kernel");
+    return PARESIS_OK;
+}
+
+// cv2.getRotationMatrix2D((w//2, h//2), angle, 1.0) followed by cv2.invertAffineTransform
+static Affine inverse_rotation(int width, int height, double angle_deg) {
+    const double ang = angle_deg * M_PI / 180.0;
+    const double al = cos(ang), be = sin(ang);
+    const double cx = width / 2, cy = height / 2;
+    const double m00 = al, m01 = be, m02 = (1 - al) * cx - be * cy;
+    const double m10 = -be, m11 = al, m12 = be * cx + (1 - al) * cy;
+    double det = m00 * m11 - m01 * m10;
+    det = det != 0 ? 1.0 / det : 0.0;
+    Affine inv;
+    inv.m[0] = m11 * det;
+    inv.m[1] = -m01 * det;
+    inv.m[3] = -m10 * det;
+    inv.m[4] = m00 * det;
+    inv.m[2] = -inv.m[0] * m02 - inv.m[1] * m12;
+    inv.m[5] = -inv.m[3] * m02 - inv.m[4] * m12;
+    return inv;
+}
+
+extern "C" int paresis_two_sphere_phantom(int kind, int dim_x, int dim_y, double pix_um, float* out3, paresis_stream stream) {
+    if (!out3 || dim_x < 1 || dim_y < 1 || !(pix_um > 0) || (kind != 0 && kind != 1)) {
+        set_last_error("paresis_two_sphere_phantom: bad arguments (kind 0 = spheres in cylinder, 1 = spheres in parallelepiped)");
+        return PARESIS_ERR_ARG;
+    }
+    const double r0_um = 500.0;                          // createSampGeom.py:126, :196
+    Phantom ph{};
+    ph.kind = kind;
+    ph.r_sphere = r0_um / pix_um;
+    ph.r_tube = 2 * r0_um / pix_um;
+    ph.ps2 = (int)ceil(ph.r_sphere);
+    int row0 = 0, col0 = 0, rotate = 0;
+    Affine inv{};
+    if (kind == 0) {
+        ph.nxp = dim_x; ph.nyp = dim_y;
+        ph.pos_y = dim_y / 2;                                                 // :128
+        ph.pos_x0 = (int)nearbyint(r0_um * 3 / pix_um);                        // :129-130 (np.round: half to even)
+        ph.pos_x1 = (int)nearbyint(r0_um * 7 / pix_um);
+    } else {
+        const int margin = (dim_x > dim_y ? dim_x : dim_y) / 2;               // :201-203
+        ph.nxp = dim_x + 2 * margin; ph.nyp = dim_y + 2 * margin;
+        ph.pos_y = ph.nyp / 2;
+        ph.pos_x0 = ph.nxp * 2 / 5;                                           // :205-206
+        ph.pos_x1 = ph.nxp * 3 / 5;
+        row0 = col0 = margin;
+        rotate = 1;
+        inv = inverse_rotation(ph.nyp, ph.nxp, 15.0);                         // :197, :243-245
+    }
+    if (2 * ph.r_sphere > ph.nxp || 2 * ph.r_sphere > ph.nyp || 2 * ph.r_tube > ph.nxp || 2 * ph.r_tube > ph.nyp) {
+        set_last_error("The sample is too big for the detector field of view (increase dimX, dimY)");   // :139, :147
+        return PARESIS_ERR_ARG;
+    }
+    // the reference assigns the sphere patches by slicing: they must fit the canvas
+    if (ph.pos_x0 - ph.ps2 < 0 || ph.pos_x1 + ph.ps2 > ph.nxp || ph.pos_y - ph.ps2 < 0 || ph.pos_y + ph.ps2 > ph.nyp) {
+        set_last_error("paresis_two_sphere_phantom: the sphere patches do not fit the canvas (could not broadcast upstream)");
+        return PARESIS_ERR_ARG;
+    }
+    phantom_kernel<<<dim3(div_up(dim_y, 128), dim_x), 128, 0, (cudaStream_t)stream>>>(ph, inv, rotate, row0, col0, pix_um * 1e-6,
+                                                                                      dim_x, dim_y, out3);
+    PARESIS_LAUNCH_CHECK("phantom_kernel");
     return PARESIS_OK;
 }
 

@@ -224,3 +224,15 @@ def sample_cylinder(radius_um, orientation_deg, dim_x, dim_y, pix):
     out = torch.empty((int(dim_x), int(dim_y)), device=device(), dtype=torch.float32)
     abi.cylinder_map(radius_um, orientation_deg, int(dim_x), int(dim_y), pix, out)
     return DeviceGeometry([out], (dim_x, dim_y))
+
+
+def sample_two_spheres(kind, dim_x, dim_y, pix):
+    """CreateSampleSpheresInCylinder (kind 0) / CreateSampleSpheresInParallelepiped (kind 1), createSampGeom.py:110-260."""
+    out = torch.empty((3, int(dim_x), int(dim_y)), device=device(), dtype=torch.float32)
+    try:
+        abi.two_sphere_phantom(kind, int(dim_x), int(dim_y), pix, out)
+    except abi.ParesisError as exc:
+        if "too big" in str(exc):
+            raise Exception('The sample is too big for the detector field of view (increase dimX, dimY)')
+        raise
+    return DeviceGeometry([out[0], out[1], out[2]], (dim_x, dim_y))

@@ -410,3 +410,16 @@ def test_detector_images_in_one_launch(abi, golden):
                 abi.detect_counts(imgs[1], os_, d0, d1, src, pk, None, expect, False)
                 abi.poisson(expect, counts, 11, 101)
                 assert torch.equal(counts, multi[1]), kcase
+
+
+def test_two_sphere_phantoms(abi, golden):
+    """CreateSampleSpheresInCylinder / CreateSampleSpheresInParallelepiped (createSampGeom.py:110-260) against the reference."""
+    g = golden("phantoms")
+    for tag, kind in (("cyl_a", 0), ("cyl_b", 0), ("par_a", 1), ("par_b", 1)):
+        dx, dy, pix = g[tag + "_cfg"]
+        out = torch.empty((3, int(dx), int(dy)), device="cuda")
+        abi.two_sphere_phantom(kind, int(dx), int(dy), float(pix), out)
+        for m in range(3):
+            assert rel_l2(out[m].cpu().numpy(), g[tag][m]) < 1e-6, (tag, m)
+    with pytest.raises(abi.ParesisError, match="too big"):
+        abi.two_sphere_phantom(0, 64, 64, 10.0, torch.empty((3, 64, 64), device="cuda"))

@@ -189,3 +189,13 @@ def test_dark_field_branch(golden):
         assert rel_l2(out, g["out_" + tag]) < 1e-12, tag
     i_out, phi_out, df = po.set_wave_rt_df(g["I"], g["phi"], g["t"], g["sw_db"][0], g["sw_db"][1], E, ["Lung", None])
     assert rel_l2(i_out, g["sw_I"]) < 1e-13 and rel_l2(phi_out, g["sw_phi"]) < 1e-13 and rel_l2(df, g["sw_df"]) < 1e-13
+
+
+def test_two_sphere_phantoms(golden):
+    """createSampGeom.py:110-260 (OpenCV's warpAffine restated for the tilted one)."""
+    g = golden("phantoms")
+    for tag, kind in (("cyl_a", 0), ("cyl_b", 0), ("par_a", 1), ("par_b", 1)):
+        dx, dy, pix = g[tag + "_cfg"]
+        got = po.sample_two_spheres(kind, int(dx), int(dy), float(pix))
+        assert got.shape == g[tag].shape
+        assert rel_l2(got, g[tag]) < 1e-12, tag
