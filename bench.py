@@ -210,6 +210,8 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run --nproc-per-node N (see module docstring)")
     torch.cuda.set_device(local)
+    from paresis_b200.hostio import affinity
+    bound = affinity.bind_to_gpu(local)        # host threads + first-touch pinned buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -348,7 +350,8 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": config_dict(l2="flushed between timed steps (256 MiB write, outside the per-step events)",
                                   timing="CUDA events per step on the launching stream, max over ranks",
-                                  wall_ms_per_step=wall / args.steps * 1e3, positions_in_flight=args.slots),
+                                  wall_ms_per_step=wall / args.steps * 1e3, positions_in_flight=args.slots,
+                                  host_cpus_bound=len(bound) if bound else None),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "pinned_buffers_allocated": transfer.pinned_allocs},
