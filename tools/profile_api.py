@@ -7,7 +7,6 @@ import pstats
 import sys
 import tempfile
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
