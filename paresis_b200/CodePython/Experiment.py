@@ -7,7 +7,8 @@ messages and the report file.  The per-energy image-formation loops
 
 Extensions read from ``exp_dict`` when present (the reference ignores unknown keys):
 ``poissonNoise`` (bool, default True), ``seed`` (int, default wall clock like Detector.py:113),
-``returnDisplacement`` (bool, default True: Dx/Dy of point 0 are copied back).
+``returnDisplacement`` (bool, default True: Dx/Dy of point 0 are copied back), ``resultDtype`` ("float64" as
+upstream, or "float32": counts are exact in float32 and cross PCIe at half the size -- what main.py saves anyway).
 """
 import time
 
@@ -256,7 +257,8 @@ class Experiment:
     def _finish(self, res, scene=None):
         """Device images -> the float64 [nbins, dimX, dimY] arrays the reference returns; images that were
         not computed (propagation / white beyond point 0) are zeros, as upstream (Experiment.py:433-434)."""
-        images = transfer.Pending(res["_stack"], torch.float64)    # one cast + one PCIe copy for all images
+        dtype = torch.float32 if str(self.exp_dict.get("resultDtype", "float64")) == "float32" else torch.float64
+        images = transfer.Pending(res["_stack"], dtype)            # one cast + one PCIe copy for all images
         if "aux" in res:
             # deferred bookkeeping: the per-energy sums and the status flag ride behind the images
             aux = transfer.Pending(res["aux"])

@@ -29,6 +29,7 @@ def run(args):
         'nbExpPoints': args.points,              # membrane positions, i.e. (Ir, Is) pairs
         'simulation_type': args.model,           # "RayT" | "Fresnel"
         'expID': datetime.datetime.now().strftime("%Y%m%d-%H%M%S"),
+        'resultDtype': "float32",                # images are saved as float32 (pagailleIO): fetch them that way
     }
     if args.seed is not None:
         exp_dict['seed'] = args.seed

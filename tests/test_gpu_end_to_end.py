@@ -240,3 +240,18 @@ def test_dark_field_branch(shim, golden):
     assert abs(e.exp_dict["meanEnergy"] / float(ge["mean_energy"]) - 1) < 1e-5
     # the sample image really differs from a non-scattering one
     assert rel_l2(res[0], ge["reference"]) > 1e-3
+
+
+def test_float32_results_option(shim):
+    """exp_dict['resultDtype'] = 'float32' (what the drop-in main.py asks for): same counts, half the bytes."""
+    outs = {}
+    for dt in ("float64", "float32"):
+        d = dict(experimentName="Small_sphere_mono", filepath="unused/", overSampling=2, nbExpPoints=1, simulation_type="RayT",
+                 expID="t", seed=5, resultDtype=dt)
+        e = shim.Experiment(d)
+        np.random.seed(4)
+        e.myMembrane.myGeometry = []
+        e.myMembrane.getMyGeometry(e.exp_dict['studyDimensions'], e.myMembrane.membranePixelSize, 2, 0, 1)
+        outs[dt] = e.computeSampleAndReferenceImages_RT(0)[:4]
+    for a, b in zip(outs["float64"], outs["float32"]):
+        assert a.dtype == np.float64 and b.dtype == np.float32 and np.array_equal(a, b.astype(np.float64))
