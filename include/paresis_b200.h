@@ -122,6 +122,26 @@ int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform
                               int nx, int ny, int margin, int* flag,
                               const paresis_refract_extras* extras_host, paresis_stream stream);
 
+/* The object hop (sample + reference beams, as paresis_refract_layers with out_ref) of up to
+ * PARESIS_MAX_GROUP energies of ONE detector bin in a single pass: inside a bin every energy repeats the hop
+ * on the same thickness maps and adds to the same accumulators (Experiment.py:448-498, :482-483), so the
+ * gradients are formed once and each energy only brings its coefficients and its own object-plane intensity
+ * image (which is cleared behind the pass, like paresis_refract_extras.clear_input).
+ *   layers[m].thickness must be the same pointers for every energy of the group;
+ *   intensity_scale   : nominal beam intensity of that energy (> 0), see paresis_refract_extras;
+ *   sum_ref           : *sum_ref += what the reference beam of that energy deposits inside the image (may be NULL). */
+#define PARESIS_MAX_GROUP 4
+typedef struct {
+    paresis_layer layers[PARESIS_MAX_LAYERS];
+    int n_layers;
+    float* intensity_in;
+    float intensity_scale;
+    double* sum_ref;
+} paresis_group_energy;
+
+int paresis_refract_group(const paresis_group_energy* energies_host, int n_energies,
+                          float* out_obj, float* out_ref, int nx, int ny, int* flag, paresis_stream stream);
+
 /* AnalyticalSample.setWaveRT as a stand-alone call (Sample.py:285-351, no dark-field branch):
  * I_out = I_in * exp(-sum atten_m t_m); phi_out = phi_in - sum phase_m t_m (phase_m = k delta_m).
  * phi_in may be NULL (0).  n = pixels. */
@@ -165,7 +185,10 @@ typedef struct {
     /* optional timing probe: cudaEvent_t pair recorded around one kernel of the first energy / bin
      * (1 = membrane hop, 2 = sample+reference hop, 3 = detector launch of the first bin); 0 = off */
     int probe; void* probe_start; void* probe_end;
-    int i_bs_dirty;            /* i_bs holds garbage: zero it first (one extra memset) */
+    int i_bs_dirty;            /* i_bs (and i_bs_group) hold garbage: zero them first (extra memsets) */
+    float* i_bs_group[PARESIS_MAX_GROUP - 1];   /* optional: further [nx][ny] buffers like i_bs (same all-zero contract).
+                                  With k of them, up to k+1 energies of a detector bin share one object hop
+                                  (paresis_refract_group); NULL entries end the list. */
 } paresis_rt_job;
 
 int paresis_rt_run(const paresis_rt_job* job_host, paresis_stream stream);
@@ -195,6 +218,7 @@ typedef struct {
     void* raster_work; size_t raster_work_bytes;
     paresis_stream stream;
     int i_bs_dirty;                /* in/out: cleared once the slot has run a position */
+    float* i_bs_group[PARESIS_MAX_GROUP - 1];   /* as in paresis_rt_job */
 } paresis_rt_slot;
 
 typedef struct {

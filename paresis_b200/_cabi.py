@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libparesis_b200.so")
 OK = 0
 FLAG_NONFINITE = 1
 MAX_LAYERS = 4
+MAX_GROUP = 4          # energies of a detector bin that can share one object hop (paresis_refract_group)
 REFRACTION_MARGIN = 15   # refractionFileNumba2.py:50
 REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
 
@@ -28,7 +29,7 @@ EXPORTS = (
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
     "paresis_two_sphere_phantom", "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
-    "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
+    "paresis_refract_group", "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
 
@@ -61,7 +62,12 @@ class RtJob(ctypes.Structure):
                 ("out_sample", ctypes.c_void_p), ("out_ref", ctypes.c_void_p), ("out_propag", ctypes.c_void_p),
                 ("out_white", ctypes.c_void_p), ("dx_pad", ctypes.c_void_p), ("dy_pad", ctypes.c_void_p),
                 ("flag", ctypes.c_void_p), ("probe", ctypes.c_int), ("probe_start", ctypes.c_void_p),
-                ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int)]
+                ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int), ("i_bs_group", ctypes.c_void_p * (MAX_GROUP - 1))]
+
+
+class GroupEnergy(ctypes.Structure):
+    _fields_ = [("layers", Layer * MAX_LAYERS), ("n_layers", ctypes.c_int), ("intensity_in", ctypes.c_void_p),
+                ("intensity_scale", ctypes.c_float), ("sum_ref", ctypes.c_void_p)]
 
 
 class RtPosition(ctypes.Structure):
@@ -74,7 +80,8 @@ class RtPosition(ctypes.Structure):
 class RtSlot(ctypes.Structure):
     _fields_ = [("i_bs", ctypes.c_void_p), ("acc_sample", ctypes.c_void_p), ("acc_ref", ctypes.c_void_p),
                 ("acc_propag", ctypes.c_void_p), ("acc_white", ctypes.c_void_p), ("raster_work", ctypes.c_void_p),
-                ("raster_work_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int)]
+                ("raster_work_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int),
+                ("i_bs_group", ctypes.c_void_p * (MAX_GROUP - 1))]
 
 
 class Membrane(ctypes.Structure):
@@ -134,6 +141,7 @@ def _load():
         "paresis_df_angle": [vp, cd, vp, sz, vp],
         "paresis_df_split": [vp, cf, vp, cf, vp, vp, vp, sz, vp],
         "paresis_df_scatter": [vp, vp, vp, ci, ci, vp],
+        "paresis_refract_group": [ctypes.POINTER(GroupEnergy), ci, vp, vp, ci, ci, vp, vp],
         "paresis_transfer_lane_create": [ctypes.POINTER(vp)],
         "paresis_transfer_lane_destroy": [vp],
         "paresis_transfer_d2h": [vp, vp, vp, sz, vp],
@@ -303,6 +311,27 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
         _ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n, _ptr(out_obj, torch.float32),
         _ptr(out_ref, torch.float32), _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
         _ptr(flag, torch.int32), ctypes.byref(extras), _stream())), "paresis_refract_layers_ex")
+    _count()
+
+
+def refract_group(energies, out_obj, out_ref, flag=None):
+    """paresis_refract_group.  energies: list of (intensity image, intensity scale, layers, sum_ref tensor or None)
+    with layers = [(thickness, grad_obj, grad_ref, atten), ...] on the same thickness maps."""
+    n = len(energies)
+    arr = (GroupEnergy * n)()
+    for g, (inten, scale, layers, sum_ref) in enumerate(energies):
+        for m, (t, go, gr, at) in enumerate(layers):
+            arr[g].layers[m].thickness = t.data_ptr()
+            arr[g].layers[m].grad_obj, arr[g].layers[m].grad_ref, arr[g].layers[m].atten = float(go), float(gr), float(at)
+            _ptr(t, torch.float32)
+        arr[g].n_layers = len(layers)
+        arr[g].intensity_in = _ptr(inten, torch.float32)
+        arr[g].intensity_scale = float(scale)
+        arr[g].sum_ref = sum_ref.data_ptr() if sum_ref is not None else None
+    nx, ny = out_obj.shape
+    _check(_timed("refract_sample_ref_hop", lambda: lib.paresis_refract_group(
+        arr, n, _ptr(out_obj, torch.float32), _ptr(out_ref, torch.float32), nx, ny, _ptr(flag, torch.int32), _stream())),
+        "paresis_refract_group")
     _count()
 
 

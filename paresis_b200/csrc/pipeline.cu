@@ -26,7 +26,12 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)job->nx * job->ny, nd = (size_t)job->det_x * job->det_y;
     const int margin = 15;   // refractionFileNumba2.py:50
-    if (job->i_bs_dirty) PARESIS_CUDA(cudaMemsetAsync(job->i_bs, 0, sizeof(float) * n, s));
+    // object-plane intensity buffers: one per energy of a group (all zero between jobs)
+    float* ibs[PARESIS_MAX_GROUP] = {job->i_bs};
+    int n_ibs = 1;
+    for (int k = 0; k < PARESIS_MAX_GROUP - 1 && job->i_bs_group[k]; ++k) ibs[n_ibs++] = job->i_bs_group[k];
+    if (job->i_bs_dirty)
+        for (int k = 0; k < n_ibs; ++k) PARESIS_CUDA(cudaMemsetAsync(ibs[k], 0, sizeof(float) * n, s));
     bool fresh_bin = true;
     int ibin = 0;
     float white = 0.f;
@@ -34,13 +39,9 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
         if (job->probe == kind && job->probe_start && job->probe_end)
             cudaEventRecord((cudaEvent_t)(start ? job->probe_start : job->probe_end), s);
     };
-    for (int e = 0; e < job->n_energies; ++e) {
+    // membrane -> object plane (Experiment.py:463-466); a fresh detector bin starts from zero accumulators
+    auto membrane_hop = [&](int e, float* dst) -> int {
         const paresis_rt_energy& en = job->energies_host[e];
-        if (en.n_hop1 < 1 || en.n_hop2 < 1 || (job->first_point && en.n_propag < 1)) {
-            set_last_error("paresis_rt_run: energy %d has an empty hop", e);
-            return PARESIS_ERR_ARG;
-        }
-        // membrane -> object plane (Experiment.py:463-466); a fresh detector bin starts from zero accumulators
         paresis_refract_extras x1{};
         if (fresh_bin) {
             x1.zero_fill[0] = job->acc_sample;
@@ -52,58 +53,110 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
         x1.zero_scalar = job->means ? job->means + e : nullptr;
         x1.intensity_scale = en.intensity_membrane;
         if (e == 0) probe(1, true);
-        int rc = paresis_refract_layers_ex(nullptr, en.intensity_membrane, en.hop1, en.n_hop1, job->i_bs, nullptr, nullptr,
-                                           nullptr, job->nx, job->ny, margin, job->flag, &x1, stream);
+        const int rc = paresis_refract_layers_ex(nullptr, en.intensity_membrane, en.hop1, en.n_hop1, dst, nullptr, nullptr, nullptr,
+                                                 job->nx, job->ny, margin, job->flag, &x1, stream);
         if (e == 0) probe(1, false);
-        if (rc) return rc;
-        // object -> detector: sample beam and reference beam in one pass over I_bs (:469-474), which is
-        // cleared behind the pass; the reference beam is summed on the way (:485-486)
-        paresis_refract_extras x2{};
-        x2.clear_input = 1;
-        x2.intensity_scale = en.intensity_membrane;
-        x2.sum_ref = job->means ? job->means + e : nullptr;
-        if (e == 0) probe(2, true);
-        rc = paresis_refract_layers_ex(job->i_bs, 0.f, en.hop2, en.n_hop2, job->acc_sample, job->acc_ref, nullptr, nullptr,
-                                       job->nx, job->ny, margin, job->flag, &x2, stream);
-        if (e == 0) probe(2, false);
-        if (rc) return rc;
-        if (job->first_point) {
-            // the sample alone (:490-498); the white field is the incident beam itself
-            const bool want_d = job->dx_pad && job->dy_pad && e == job->n_energies - 1;
-            if (want_d) {
-                const size_t np = (size_t)(job->nx + 2 * margin) * (job->ny + 2 * margin);
-                PARESIS_CUDA(cudaMemsetAsync(job->dx_pad, 0, sizeof(float) * np, s));
-                PARESIS_CUDA(cudaMemsetAsync(job->dy_pad, 0, sizeof(float) * np, s));
-            }
-            paresis_refract_extras x3{};
-            x3.intensity_scale = en.intensity_propag;
-            rc = paresis_refract_layers_ex(nullptr, en.intensity_propag, en.propag, en.n_propag, job->acc_propag, nullptr,
-                                           want_d ? job->dx_pad : nullptr, want_d ? job->dy_pad : nullptr, job->nx, job->ny,
-                                           margin, job->flag, &x3, stream);
-            if (rc) return rc;
-            white += en.intensity_propag;
+        return rc;
+    };
+    // the sample alone (:490-498); the white field is the incident beam itself
+    auto propagation_hop = [&](int e) -> int {
+        const paresis_rt_energy& en = job->energies_host[e];
+        const bool want_d = job->dx_pad && job->dy_pad && e == job->n_energies - 1;
+        if (want_d) {
+            const size_t np = (size_t)(job->nx + 2 * margin) * (job->ny + 2 * margin);
+            PARESIS_CUDA(cudaMemsetAsync(job->dx_pad, 0, sizeof(float) * np, s));
+            PARESIS_CUDA(cudaMemsetAsync(job->dy_pad, 0, sizeof(float) * np, s));
         }
-        if (en.close_bin) {   // :501-521
-            const uint64_t seq = job->sequence + (uint64_t)ibin * 4;
-            float* const imgs[4] = {job->acc_sample, job->acc_ref, job->acc_propag, job->acc_white};
-            float* const outs[4] = {job->out_sample, job->out_ref, job->out_propag, job->out_white};
-            const int count = job->first_point ? 4 : 2;
+        paresis_refract_extras x3{};
+        x3.intensity_scale = en.intensity_propag;
+        const int rc = paresis_refract_layers_ex(nullptr, en.intensity_propag, en.propag, en.n_propag, job->acc_propag, nullptr,
+                                                 want_d ? job->dx_pad : nullptr, want_d ? job->dy_pad : nullptr, job->nx, job->ny,
+                                                 margin, job->flag, &x3, stream);
+        white += en.intensity_propag;
+        return rc;
+    };
+    // all images of the bin in one launch (Detector.detection is called once per image, :501-521)
+    auto close_bin = [&]() -> int {
+        const uint64_t seq = job->sequence + (uint64_t)ibin * 4;
+        float* const imgs[4] = {job->acc_sample, job->acc_ref, job->acc_propag, job->acc_white};
+        float* const outs[4] = {job->out_sample, job->out_ref, job->out_propag, job->out_white};
+        const int count = job->first_point ? 4 : 2;
+        int rc = PARESIS_OK;
+        if (job->first_point) {
+            rc = paresis_fill(job->acc_white, white, n, stream);
+            if (rc) return rc;
+        }
+        const float* in_k[4]; float* out_k[4]; uint64_t seq_k[4];
+        for (int k = 0; k < count; ++k) { in_k[k] = imgs[k]; out_k[k] = outs[k] + (size_t)ibin * nd; seq_k[k] = seq + k; }
+        if (ibin == 0) probe(3, true);
+        rc = paresis_detect_counts_multi(in_k, out_k, seq_k, count, job->nx, job->ny, job->oversampling, job->det_x,
+                                         job->det_y, job->src_kernel, job->src_half, job->psf_kernel, job->psf_half,
+                                         job->detect_work, job->noise, job->seed, stream);
+        if (ibin == 0) probe(3, false);
+        ++ibin;
+        fresh_bin = true;
+        return rc;
+    };
+    auto same_maps = [&](const paresis_rt_energy& p, const paresis_rt_energy& q) {
+        if (p.n_hop2 != q.n_hop2) return false;
+        for (int m = 0; m < p.n_hop2; ++m)
+            if (p.hop2[m].thickness != q.hop2[m].thickness) return false;
+        return true;
+    };
+    for (int e = 0; e < job->n_energies;) {
+        const paresis_rt_energy& en = job->energies_host[e];
+        if (en.n_hop1 < 1 || en.n_hop2 < 1 || (job->first_point && en.n_propag < 1)) {
+            set_last_error("paresis_rt_run: energy %d has an empty hop", e);
+            return PARESIS_ERR_ARG;
+        }
+        // energies of the same detector bin that share their maps go through the object hop together
+        int group = 1;
+        while (group < n_ibs && e + group < job->n_energies && !job->energies_host[e + group - 1].close_bin &&
+               job->energies_host[e + group].n_hop1 >= 1 && same_maps(en, job->energies_host[e + group]))
+            ++group;
+        int rc;
+        if (group == 1) {
+            rc = membrane_hop(e, job->i_bs);
+            if (rc) return rc;
+            // object -> detector: sample beam and reference beam in one pass over I_bs (:469-474), which is
+            // cleared behind the pass; the reference beam is summed on the way (:485-486)
+            paresis_refract_extras x2{};
+            x2.clear_input = 1;
+            x2.sum_ref = job->means ? job->means + e : nullptr;
+            x2.intensity_scale = en.intensity_membrane;
+            if (e == 0) probe(2, true);
+            rc = paresis_refract_layers_ex(job->i_bs, 0.f, en.hop2, en.n_hop2, job->acc_sample, job->acc_ref, nullptr, nullptr,
+                                           job->nx, job->ny, margin, job->flag, &x2, stream);
+            if (e == 0) probe(2, false);
+            if (rc) return rc;
+        } else {
+            paresis_group_energy ge[PARESIS_MAX_GROUP];
+            for (int g = 0; g < group; ++g) {
+                rc = membrane_hop(e + g, ibs[g]);
+                if (rc) return rc;
+                const paresis_rt_energy& eg = job->energies_host[e + g];
+                for (int m = 0; m < eg.n_hop2; ++m) ge[g].layers[m] = eg.hop2[m];
+                ge[g].n_layers = eg.n_hop2;
+                ge[g].intensity_in = ibs[g];
+                ge[g].intensity_scale = eg.intensity_membrane;
+                ge[g].sum_ref = job->means ? job->means + e + g : nullptr;
+            }
+            if (e == 0) probe(2, true);
+            rc = paresis_refract_group(ge, group, job->acc_sample, job->acc_ref, job->nx, job->ny, job->flag, stream);
+            if (e == 0) probe(2, false);
+            if (rc) return rc;
+        }
+        for (int g = 0; g < group; ++g) {
             if (job->first_point) {
-                rc = paresis_fill(job->acc_white, white, n, stream);
+                rc = propagation_hop(e + g);
                 if (rc) return rc;
             }
-            // all images of the bin in one launch (Detector.detection is called once per image, :503-514)
-            const float* in_k[4]; float* out_k[4]; uint64_t seq_k[4];
-            for (int k = 0; k < count; ++k) { in_k[k] = imgs[k]; out_k[k] = outs[k] + (size_t)ibin * nd; seq_k[k] = seq + k; }
-            if (ibin == 0) probe(3, true);
-            rc = paresis_detect_counts_multi(in_k, out_k, seq_k, count, job->nx, job->ny, job->oversampling, job->det_x,
-                                             job->det_y, job->src_kernel, job->src_half, job->psf_kernel, job->psf_half,
-                                             job->detect_work, job->noise, job->seed, stream);
-            if (ibin == 0) probe(3, false);
-            if (rc) return rc;
-            ++ibin;
-            fresh_bin = true;
         }
+        if (job->energies_host[e + group - 1].close_bin) {   // :501-521
+            rc = close_bin();
+            if (rc) return rc;
+        }
+        e += group;
     }
     return PARESIS_OK;
 }
@@ -183,6 +236,7 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
         j.energies_host = energies.data();
         j.first_point = pos.first_point;
         j.i_bs = slot.i_bs; j.acc_sample = slot.acc_sample; j.acc_ref = slot.acc_ref;
+        for (int k = 0; k < PARESIS_MAX_GROUP - 1; ++k) j.i_bs_group[k] = slot.i_bs_group[k];
         j.acc_propag = slot.acc_propag; j.acc_white = slot.acc_white;
         j.i_bs_dirty = slot.i_bs_dirty;
         j.means = pos.means;

@@ -99,6 +99,7 @@ class ImageFormation:
         f32 = dict(device=self.device, dtype=torch.float32)
         n = (self.nx, self.ny)
         self.i_bs = torch.zeros(n, **f32)      # invariant of paresis_rt_run: all zero between jobs
+        self.i_bs_group = []                   # further such buffers, made when a detector bin holds several energies
         self._i_bs_dirty = False
         self.acc = {k: torch.zeros(n, **f32) for k in IMAGES}
         self.work = torch.empty(abi.detect_work_floats(self.nx, self.ny, self.os, self.det_x, self.det_y), **f32)
@@ -229,6 +230,8 @@ class ImageFormation:
         job.first_point, job.n_energies, job.energies_host = int(first), len(energies), energies
         job.i_bs = self.i_bs.data_ptr()
         job.i_bs_dirty = 1 if self._i_bs_dirty else 0
+        for k, t in enumerate(self._group_buffers(scene)):
+            job.i_bs_group[k] = t.data_ptr()
         job.acc_sample, job.acc_ref = self.acc["sample"].data_ptr(), self.acc["reference"].data_ptr()
         job.acc_propag, job.acc_white = self.acc["propag"].data_ptr(), self.acc["white"].data_ptr()
         job.means, job.detect_work = self.means.data_ptr(), self.work.data_ptr()
@@ -237,6 +240,14 @@ class ImageFormation:
         job.noise, job.seed, job.sequence = int(self.poisson), self.seed, sequence
         job.flag = self.flag.data_ptr()
         return job, (src, psf)
+
+    def _group_buffers(self, scene, owner=None):
+        """Extra object-plane buffers so that up to MAX_GROUP energies of a detector bin share one object hop."""
+        want = min(abi.MAX_GROUP, max((len(b) for b in self.bins(scene)), default=1)) - 1
+        store = self.i_bs_group if owner is None else owner.setdefault("i_bs_group", [])
+        while len(store) < want:
+            store.append(torch.zeros((self.nx, self.ny), device=self.device, dtype=torch.float32))
+        return store[:want]
 
     @staticmethod
     def sequence(point_num, sequence_base=0):
@@ -350,6 +361,8 @@ class ImageFormation:
             sl.raster_work, sl.raster_work_bytes = c["work"].data_ptr(), c["work"].numel()
             sl.stream = c["stream"].cuda_stream
             sl.i_bs_dirty = 1 if (c["dirty"] or (k == 0 and self._i_bs_dirty)) else 0
+            for kk, t in enumerate(self._group_buffers(s, owner=None if k == 0 else c)):
+                sl.i_bs_group[kk] = t.data_ptr()
             c["dirty"] = True
         self._i_bs_dirty = True
         offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(n_pos, plan.layers, 2))

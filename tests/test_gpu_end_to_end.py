@@ -247,11 +247,12 @@ def test_float32_results_option(shim):
     outs = {}
     for dt in ("float64", "float32"):
         d = dict(experimentName="Small_sphere_mono", filepath="unused/", overSampling=2, nbExpPoints=1, simulation_type="RayT",
-                 expID="t", seed=5, resultDtype=dt)
+                 expID="t", poissonNoise=False, resultDtype=dt)
         e = shim.Experiment(d)
         np.random.seed(4)
         e.myMembrane.myGeometry = []
         e.myMembrane.getMyGeometry(e.exp_dict['studyDimensions'], e.myMembrane.membranePixelSize, 2, 0, 1)
         outs[dt] = e.computeSampleAndReferenceImages_RT(0)[:4]
     for a, b in zip(outs["float64"], outs["float32"]):
-        assert a.dtype == np.float64 and b.dtype == np.float32 and np.array_equal(a, b.astype(np.float64))
+        # (two runs: the fp32 accumulation order of the few rays that bypass the tiles is not reproducible)
+        assert a.dtype == np.float64 and b.dtype == np.float32 and rel_l2(b, a) < 1e-6

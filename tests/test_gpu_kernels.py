@@ -423,3 +423,39 @@ def test_two_sphere_phantoms(abi, golden):
             assert rel_l2(out[m].cpu().numpy(), g[tag][m]) < 1e-6, (tag, m)
     with pytest.raises(abi.ParesisError, match="too big"):
         abi.two_sphere_phantom(0, 64, 64, 10.0, torch.empty((3, 64, 64), device="cuda"))
+
+
+@pytest.mark.parametrize("shape,n_e", [((130, 290), 2), ((300, 257), 4), ((517, 1030), 3)])
+def test_energy_group_hop_matches_energy_by_energy(abi, shape, n_e):
+    """paresis_refract_group (several energies of a detector bin through the object hop at once) against the
+    same energies one by one (paresis_refract_layers with out_ref), accumulating into the same images."""
+    rng = np.random.default_rng(9)
+    x = np.linspace(0, 9, shape[0])[:, None]
+    y = np.linspace(0, 9, shape[1])[None, :]
+    caps = np.sqrt(np.maximum(0.0, 0.2 - (np.mod(x, 1.0) - 0.5) ** 2 - (np.mod(y, 1.0) - 0.5) ** 2))
+    tm, ts = dev((6e-4 * caps).astype(np.float32)), dev((9e-4 * np.exp(-((x - 4.5) ** 2 + (y - 4.2) ** 2))).astype(np.float32))
+    pix, M, d3 = 2.9256, 1.0254, 3.6
+    energies, scales = [30.0, 41.0, 52.0, 67.0][:n_e], [900.0, 4200.0, 7500.0, 150.0][:n_e]
+    ref_s = torch.zeros(shape, device="cuda"); ref_r = torch.zeros(shape, device="cuda")
+    got_s = torch.zeros(shape, device="cuda"); got_r = torch.zeros(shape, device="cuda")
+    group, sums, want_sums = [], [], []
+    for E, i0 in zip(energies, scales):
+        dm, ds = 5.97e-7 * (52.0 / E) ** 2, 9.52e-8 * (52.0 / E) ** 2
+        g3m, _ = _layer_coeffs([dm], [0.0], E, d3, M, pix)
+        g3s, a3s = _layer_coeffs([ds], [4.4e-11 * (52.0 / E) ** 3], E, d3, M, pix)
+        layers = [(tm, g3m[0], g3m[0], 0.0), (ts, g3s[0], 0.0, a3s[0])]
+        i_in = (i0 * (0.6 + 0.8 * rng.random(shape))).astype(np.float32)
+        i_in[rng.random(shape) > 0.997] *= 3.0          # brighter than 2 x its scale: fp32 path
+        before = ref_r.double().sum().item()
+        abi.refract_layers(dev(i_in), 0.0, layers, ref_s, ref_r)
+        want_sums.append(ref_r.double().sum().item() - before)
+        sums.append(torch.full((1,), 2.0, device="cuda", dtype=torch.float64))
+        group.append((dev(i_in), i0, layers, sums[-1]))
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    abi.refract_group(group, got_s, got_r, flag)
+    assert int(flag.item()) == 0
+    assert rel_l2(got_s.cpu().numpy(), ref_s.cpu().numpy()) < 3e-6
+    assert rel_l2(got_r.cpu().numpy(), ref_r.cpu().numpy()) < 3e-6
+    for (inten, _, _, _), s_, w in zip(group, sums, want_sums):
+        assert not inten.any()                                      # cleared behind the pass
+        assert abs((s_.item() - 2.0) / w - 1) < 1e-5
