@@ -43,5 +43,7 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
 
 // Fixed-point shared-memory tile kernel (refract_tile.cu): tiles of up to 16 source rows x 256 columns, halo 4.
 int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
+// The same with fewer instructions per ray (refract_lean.cu): integer bilinear split, deferred misses.
+int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 
 }  // namespace paresis

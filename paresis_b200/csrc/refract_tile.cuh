@@ -47,6 +47,37 @@ struct TileTarget {
     int rlo, clo;          // image coordinates of tile cell (0, 0)
 };
 
+// One ray straight to L2 in fp32, cell by cell; cells outside the image are dropped, which is what zero-padding,
+// scattering and cropping does (refractionFileNumba2.py:65-78; the |D| > N kill of :61-64 only removes rays that
+// land outside anyway).  Returns what was deposited inside the image.  TWIN: the same ray goes to `out2` as well.
+template <bool TWIN>
+__device__ __forceinline__ float deposit_direct(float* out, float* out2, int i, int j, float v, float dx, float dy, int nx, int ny,
+                                                bool& bad) {
+    const float flx = floorf(dx), fly = floorf(dy);
+    const float fx = dx - flx, fy = dy - fly;
+    const int r = i + __float2int_rd(dx), c = j + __float2int_rd(dy);   // saturating
+    const float v1 = v * fx, v0 = v - v1;
+    const float w1 = v0 * fy, w0 = v0 - w1, w3 = v1 * fy, w2 = v1 - w3;
+    bad |= !(fabsf(w0 + w3) <= 3.0e38f);
+    const bool ra = (unsigned)r < (unsigned)nx, rb = (unsigned)(r + 1) < (unsigned)nx;
+    const bool ca = (unsigned)c < (unsigned)ny, cb = (unsigned)(c + 1) < (unsigned)ny;
+    const long long o = (long long)r * ny + c;
+    float* p = out + o;
+    float sum = 0.f;
+    if (ra && ca && w0 != 0.f) { red_add(p, w0); sum += w0; }
+    if (ra && cb && w1 != 0.f) { red_add(p + 1, w1); sum += w1; }
+    if (rb && ca && w2 != 0.f) { red_add(p + ny, w2); sum += w2; }
+    if (rb && cb && w3 != 0.f) { red_add(p + ny + 1, w3); sum += w3; }
+    if (TWIN) {
+        float* q = out2 + o;
+        if (ra && ca && w0 != 0.f) red_add(q, w0);
+        if (ra && cb && w1 != 0.f) red_add(q + 1, w1);
+        if (rb && ca && w2 != 0.f) red_add(q + ny, w2);
+        if (rb && cb && w3 != 0.f) red_add(q + ny + 1, w3);
+    }
+    return sum;
+}
+
 // One ray.  Fast path: fixed-point deposit into the tile (native ATOMS.ADD).  Everything else -- the ray leaves
 // the tile, touches the image border, is too bright / negative / not finite -- goes to L2 in fp32, cell by cell;
 // cells outside the image are dropped, which is what zero-padding, scattering and cropping does
@@ -82,36 +113,15 @@ __device__ __forceinline__ float deposit(const TileTarget& t, int i, int j, floa
         }
         return v;
     }
-    float sum = 0.f;
-    if (live) {
-        const float v1 = v * fx, v0 = v - v1;
-        const float w1 = v0 * fy, w0 = v0 - w1, w3 = v1 * fy, w2 = v1 - w3;
-        bad |= !(fabsf(w0 + w3) <= 3.0e38f);
-        const bool ra = (unsigned)r < (unsigned)nx, rb = (unsigned)(r + 1) < (unsigned)nx;
-        const bool ca = (unsigned)c < (unsigned)ny, cb = (unsigned)(c + 1) < (unsigned)ny;
-        const long long o = (long long)r * ny + c;
-        float* p = t.out + o;
-        if (ra && ca && w0 != 0.f) { red_add(p, w0); sum += w0; }
-        if (ra && cb && w1 != 0.f) { red_add(p + 1, w1); sum += w1; }
-        if (rb && ca && w2 != 0.f) { red_add(p + ny, w2); sum += w2; }
-        if (rb && cb && w3 != 0.f) { red_add(p + ny + 1, w3); sum += w3; }
-        if (TWIN) {
-            float* q = out2 + o;
-            if (ra && ca && w0 != 0.f) red_add(q, w0);
-            if (ra && cb && w1 != 0.f) red_add(q + 1, w1);
-            if (rb && ca && w2 != 0.f) red_add(q + ny, w2);
-            if (rb && cb && w3 != 0.f) red_add(q + ny + 1, w3);
-        }
-    }
-    return sum;
+    return live ? deposit_direct<TWIN>(t.out, out2, i, j, v, dx, dy, nx, ny, bad) : 0.f;
 }
 
 // Tile -> image: dense 128-bit REDs, all-zero quads skipped; image borders and odd pitches fall back to scalars.
 template <int SR, int SC>
 __device__ __forceinline__ void flush_tile(const unsigned* tile, float* out, int rlo, int clo, int nx, int ny, float inv_scale,
-                                           bool vec_ok) {
+                                           bool vec_ok, int nrows = SR) {
     constexpr int Q = SC / 4;
-    for (int idx = threadIdx.x; idx < SR * Q; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < nrows * Q; idx += blockDim.x) {
         const int sr = idx / Q, q4 = idx - sr * Q;
         const int r = rlo + sr, c = clo + 4 * q4;
         if ((unsigned)r >= (unsigned)nx) continue;

@@ -299,11 +299,21 @@ def test_poisson_statistics(abi):
     assert torch.equal(d, a[:1000])
 
 
-@pytest.mark.parametrize("shape", [(130, 290), (300, 257), (40, 36), (517, 1030)])
-def test_tile_hop_kernel_matches_direct_kernel(abi, shape):
-    """The fixed-point shared-memory tile kernel (intensity_scale given) against the fp32 direct-to-L2
+@pytest.fixture
+def tile_config(abi, request):
+    """0 = lean tile kernel (refract_lean.cuh, production), 1 = first tile kernel (refract_tile.cuh)."""
+    abi.set_tuning(2, request.param)
+    yield request.param
+    abi.set_tuning(2, 0)
+
+
+@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+@pytest.mark.parametrize("shape", [(130, 290), (300, 257), (40, 36), (517, 1030), (96, 2048)])
+def test_tile_hop_kernel_matches_direct_kernel(abi, shape, tile_config):
+    """The fixed-point shared-memory tile kernels (intensity_scale given) against the fp32 direct-to-L2
     kernel on the same inputs: membrane-like torn field, rays brighter than 2 x scale, negative rays,
-    ragged / odd sizes; plus the pipeline extras (zero-fill, clear-input, reference-beam sum)."""
+    ragged / odd sizes (border warps and rows, the miss list, unaligned zero-fill); plus the pipeline
+    extras (zero-fill, clear-input, reference-beam sum)."""
     rng = np.random.default_rng(5)
     x = np.linspace(0, 9, shape[0])[:, None]
     y = np.linspace(0, 9, shape[1])[None, :]
@@ -343,7 +353,8 @@ def test_tile_hop_kernel_matches_direct_kernel(abi, shape):
     assert int(flag.item()) & abi.FLAG_NONFINITE
 
 
-def test_tile_hop_kernel_cannot_overflow(abi):
+@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+def test_tile_hop_kernel_cannot_overflow(abi, tile_config):
     """Every ray of a tile focused into ONE cell (a lens): the fixed-point tile holds it (rays per tile x
     brightest fixed-point ray < 2^32) and the image gets the exact sum."""
     n = 256
@@ -362,7 +373,7 @@ def test_tile_hop_kernel_cannot_overflow(abi):
     assert abs(out.double().sum().item() / ref.double().sum().item() - 1) < 1e-5
     assert abs(out.double().sum().item() / (n * n * 1.9 * i0) - 1) < 1e-5    # (four fp32 cells of ~3e7 each: ulp = 2)
     assert out.max().item() > 0.2 * n * n * 1.9 * i0          # really focused
-    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5     # (two fp32 scheduling orders of the same sums)
 
 
 def test_membrane_from_field_matches_raster(abi):
