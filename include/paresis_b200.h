@@ -55,7 +55,10 @@ int paresis_set_tuning(int key, int value);
  * (dx, dy) pixels.  `margin` is the virtual zero padding of the loop frame: 0 reproduces a
  * direct call (edge quirk of :238-262 included), 15 / 10 what fastRefraction v2 / v1 see
  * after pad + crop (refractionFileNumba2.py:65-78).  `variant`: 0 = plain REDs,
- * 1 = warp-aggregated rows, 2 = warp-aggregated rows + register-carried columns (default). */
+ * 1 = warp-aggregated rows, 2 = warp-aggregated rows + register-carried columns (default),
+ * 3 = fixed-point shared-memory tiles with a dense flush (the one for torn displacement fields such as a
+ * membrane's; deposits are quantised to 2^-19 ... 2^-18 of the mean ray of each 16 x 256 source tile, rays
+ * brighter than twice that mean bypass the tiles). */
 int paresis_splat(const float* intensity, const float* dx, const float* dy, float* out,
                   int nx, int ny, int margin, int variant, int* flag, paresis_stream stream);
 

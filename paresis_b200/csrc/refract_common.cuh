@@ -46,4 +46,7 @@ int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_
 // The same with fewer instructions per ray (refract_lean.cu): integer bilinear split, deferred misses.
 int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 
+// Stand-alone splat through fixed-point shared-memory tiles (splat_tile.cu): variant 3 of paresis_splat.
+int launch_splat_tile(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, cudaStream_t s);
+
 }  // namespace paresis

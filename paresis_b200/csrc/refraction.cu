@@ -278,6 +278,7 @@ extern "C" int paresis_splat(const float* intensity, const float* dx, const floa
         case 0: splat_kernel<0><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
         case 1: splat_kernel<1><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
         case 2: splat_kernel<2><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
+        case 3: return launch_splat_tile(intensity, dx, dy, out, f, flag, s);
         default: set_last_error("paresis_splat: unknown variant %d", variant); return PARESIS_ERR_ARG;
     }
     PARESIS_LAUNCH_CHECK("splat_kernel");

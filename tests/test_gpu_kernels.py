@@ -36,7 +36,11 @@ def run_splat(abi, I, Dx, Dy, margin, variant):
     return out.cpu().numpy().astype(np.float64), int(flag.item())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+# variant 3 (fixed-point shared-memory tiles) quantises deposits to 2^-19 ... 2^-18 of the mean ray of a tile
+SPLAT_TOL = {0: 1.0, 1: 1.0, 2: 1.0, 3: 10.0}
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_splat_known_answers(abi, golden, variant):
     g = golden("splat_kernel")
     for row in g["known_answers"]:
@@ -53,18 +57,19 @@ def test_splat_known_answers(abi, golden, variant):
     assert np.array_equal(got, g["edge_quirk"])  # the reference's edge quirk, bit for bit
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_splat_reference_frames(abi, golden, variant, tag):
     g = golden("splat_kernel")
     got, flag = run_splat(abi, g["I_" + tag], g["Dx_" + tag], g["Dy_" + tag], 0, variant)
     assert flag == 0
-    assert rel_l2(got, g["out_" + tag]) < 2e-6  # inputs are fp64 goldens rounded to fp32 (|D| up to ~100 px)
+    assert rel_l2(got, g["out_" + tag]) < 2e-6 * max(1.0, SPLAT_TOL[variant] / 3)  # inputs are fp64 goldens rounded to fp32 (|D| up to ~100 px)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape,amp,margin", [((257, 300), 0.7, 15), ((64, 1030), 9.0, 15), ((513, 96), 30.0, 0),
-                                               ((40, 33), 100.0, 10), ((3, 3), 1.0, 0), ((1, 70), 2.0, 0)])
+                                               ((40, 33), 100.0, 10), ((3, 3), 1.0, 0), ((1, 70), 2.0, 0),
+                                               ((700, 1100), 2.5, 15)])
 def test_splat_vs_oracle(abi, variant, shape, amp, margin):
     rng = np.random.default_rng(hash((shape, margin)) % 1000)
     x = np.linspace(0, 6, shape[0])[:, None]
@@ -79,17 +84,16 @@ def test_splat_vs_oracle(abi, variant, shape, amp, margin):
     want = po.splat(I, Dx, Dy, margin)
     got, flag = run_splat(abi, I, Dx, Dy, margin, variant)
     assert flag == 0
-    assert rel_l2(got, want) < 5e-7
-    if margin == 0 and amp < 1:
-        pass
+    assert rel_l2(got, want) < 5e-7 * SPLAT_TOL[variant]
     # conservation: what stays inside the frame is what the oracle says stays
     assert abs(got.sum() / want.sum() - 1) < 1e-6
 
 
 def test_splat_flags_nonfinite(abi):
     I = np.ones((16, 40)); I[3, 3] = np.nan
-    _, flag = run_splat(abi, I, np.zeros((16, 40)), np.zeros((16, 40)), 15, 2)
-    assert flag & abi.FLAG_NONFINITE
+    for variant in (2, 3):
+        _, flag = run_splat(abi, I, np.zeros((16, 40)), np.zeros((16, 40)), 15, variant)
+        assert flag & abi.FLAG_NONFINITE
 
 
 def test_splat_large_conservation(abi):
@@ -101,12 +105,21 @@ def test_splat_large_conservation(abi):
     I = torch.ones((n, n), device="cuda")
     I[:8] = 0; I[-8:] = 0; I[:, :8] = 0; I[:, -8:] = 0
     outs = []
-    for variant in (0, 2):
+    for variant in (0, 2, 3):
         out = torch.zeros((n, n), device="cuda")
         abi.splat(I, Dx, Dy, out, margin=15, variant=variant)
         outs.append(out)
         assert abs(out.double().sum().item() / I.double().sum().item() - 1) < 1e-6
     assert rel_l2(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6
+    assert rel_l2(outs[2].cpu().numpy(), outs[0].cpu().numpy()) < 2e-6
+    # negative and very unequal intensities, `out +=` on a non-zero image: the tile variant against plain REDs
+    I2 = (I * (1.0 + 50.0 * (torch.rand((n, n), device="cuda") > 0.999))).contiguous()
+    I2[100:110, 200:260] = -3.0
+    base = torch.rand((n, n), device="cuda")
+    a, b = base.clone(), base.clone()
+    abi.splat(I2, Dx, Dy, a, margin=15, variant=0)
+    abi.splat(I2, Dx, Dy, b, margin=15, variant=3)
+    assert rel_l2((b - base).cpu().numpy(), (a - base).cpu().numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("tag", ["sub", "mid", "far", "huge"])

@@ -47,6 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", type=int, nargs="+", default=[2048, 4096, 8192])
     ap.add_argument("--out", default="gpurun_out/microbench.json")
+    ap.add_argument("--splat-only", action="store_true", help="copy / memset and the stand-alone splat variants only")
     args = ap.parse_args()
     dev = "cuda"
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # 256 MiB > 126 MB L2
@@ -106,10 +107,14 @@ def main():
         for fname, (Dx, Dy) in fields.items():
             frac_moved = float(((Dx != 0) | (Dy != 0)).float().mean().item())
             p99 = float(torch.quantile(torch.maximum(Dx.abs(), Dy.abs()).flatten()[:: max(1, px // 1000000)], 0.99).item())
-            for variant in (0, 1, 2):
+            for variant in (0, 1, 2, 3):
                 med, best = timeit(lambda: abi.splat(a, Dx, Dy, out, margin=15, variant=variant), flush=flush)
                 rec("splat_v%d" % variant, n, med, best, 16 * px, field=fname, moved=frac_moved, p99=p99)
         del fields
+        if args.splat_only:
+            del a, b, out, t_mem, sph
+            torch.cuda.empty_cache()
+            continue
         # fused kernels on the real membrane map
         s2 = hm.refraction_gradient_scale(1.6, 1.0254, 2.9256)
         s3 = hm.refraction_gradient_scale(3.6, 1.0254, 2.9256)
