@@ -363,11 +363,55 @@ def run_gpu(args):
                                  "the GPU (the other %d in flight drain first), so the interval is this kernel only" % (args.slots - 1)},
             "kernel_shares": shares,
         }
+        if world == 1:
+            line["splat"] = splat_roofline(abi, geometry, exp, torch, flush, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def splat_roofline(abi, geometry, exp, torch, flush, peak):
+    """BASELINE.json's second figure: the stand-alone refraction splat (paresis_splat = fastloopNumba: read I, Dx, Dy,
+    out += ; 16 algorithmic bytes per study pixel) on the displacement field of one membrane position,
+    at the workload grid and at a DRAM-resident one.  CUDA events per launch, L2 flushed before each, median of 10."""
+    from paresis_b200 import hostmath as hm
+    mem = exp.myMembrane
+    pix = float(exp.exp_dict["studyPixelSize"])
+    k = hm.wavenumber(52e3)
+    delta = 5.97e-7        # CuSn at 52 keV (TablesDeltaBeta.xls)
+    out = {"kernel": "paresis_splat", "alg_bytes_per_pixel": 16, "field": "membrane displacement of one position (object hop)",
+           "unit": "GB/s", "peak": peak, "grids": {}}
+    for n in (2048, 8192):
+        np.random.seed(n)
+        geom, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, 1, mem.myPMMAThickness)
+        phi = (-(k * delta) * geom.entries[0].double()).contiguous()
+        dxp = torch.zeros((n + 30, n + 30), device="cuda"); dyp = torch.zeros_like(dxp)
+        inten = torch.full((n, n), 7500.0, device="cuda")
+        tmp = torch.zeros((n, n), device="cuda")
+        abi.refract_phi(inten, phi, tmp, 3.6, 52.0, float(exp.exp_dict["magnification"]), pix, 15, dxp, dyp)
+        dx = dxp[15:-15, 15:-15].contiguous(); dy = dyp[15:-15, 15:-15].contiguous()
+        del dxp, dyp, phi, geom
+        inten = (inten * (0.7 + 0.6 * torch.rand((n, n), device="cuda"))).contiguous()
+        res = {"mean_abs_displacement_px": float((dx.abs().mean() + dy.abs().mean()).item() / 2)}
+        for variant, label in ((2, "direct_red"), (3, "smem_tiles")):
+            for _ in range(3):
+                abi.splat(inten, dx, dy, tmp, margin=15, variant=variant)
+            times = []
+            for _ in range(10):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); abi.splat(inten, dx, dy, tmp, margin=15, variant=variant); e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            ms = float(np.median(times))
+            gbs = 16.0 * n * n / (ms * 1e-3) / 1e9
+            res[label] = {"variant": variant, "avg_launch_ms": ms, "achieved": gbs, "frac": gbs / peak}
+        out["grids"][str(n)] = res
+        del dx, dy, inten, tmp
+        torch.cuda.empty_cache()
+    return out
 
 
 def profile_kernels(abi, job, torch):
