@@ -7,9 +7,9 @@
 // its rays into a tile covering the source tile plus a 4-pixel halo with native 32-bit integer shared-memory atomics,
 // and the tile leaves the SM as dense 128-bit REDs (refract_lean.cuh has the deposit and the flush).
 //
-// The API carries no intensity scale, so each block takes its own: the intensities of its tile are loaded first
-// (16 registers per thread); twice their mean (over the finite positive ones) = 1.x * 2^e gives the unit 2^(e - 19),
-// rays below 2^(e+1) take the tile, and 4096 rays of less than 2^20 units cannot overflow a 32-bit cell.  Rays that
+// The API carries no intensity scale, so each block takes its own from a quarter of its rows: twice the mean of
+// their finite positive intensities = 1.x * 2^e gives the unit 2^(e - 19), rays below 2^(e+1) take the tile, and
+// 4096 rays of less than 2^20 units cannot overflow a 32-bit cell.  Rays that
 // are brighter, leave the tile window, touch the image border, are negative or not finite go through make_ray() --
 // the reference's loop-frame rules -- straight to L2, from a list, once the block is through its rows.
 #include "refract_lean.cuh"
@@ -17,7 +17,7 @@
 namespace paresis {
 
 template <int TR, int MQ>
-__global__ void __launch_bounds__(TILE_COLS, 4)
+__global__ void __launch_bounds__(TILE_COLS, 6)
 splat_tile_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const float* __restrict__ Dy, float* __restrict__ out,
                   Frame f, int rows, int* flag) {
     constexpr int H = 4, SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H, U = 4;
@@ -38,22 +38,24 @@ splat_tile_kernel(const float* __restrict__ I, const float* __restrict__ Dx, con
         for (int k = tid; k < used_rows * (SC / 4); k += TILE_COLS) z[k] = make_uint4(0u, 0u, 0u, 0u);
         if (tid == 0) *qcount = 0u;
     }
-    const size_t col0 = (size_t)i0 * f.ny + jc;
+    const int nrows = i1 - i0;
+    const int col0 = i0 * f.ny + jc, last = col0 + (nrows - 1) * f.ny;      // nx * ny < 2^30 (host check)
 
-    // the tile's intensities and their scale
-    float v[TR];
+    // the scale of the tile from a quarter of its rows, and the first rows of the walk
     float m = 0.f;
 #pragma unroll
-    for (int u = 0; u < TR; ++u) {
-        v[u] = (i0 + u < i1) ? __ldg(I + col0 + (size_t)u * f.ny) : 0.f;
-        if (live && v[u] > 0.f && v[u] < 3.0e38f) m += v[u];     // NaN fails the compares
+    for (int k = 0; k < 4; ++k) {
+        const float t = __ldg(I + min(col0 + k * (TR / 4) * f.ny, last));
+        if (live && t > 0.f && t < 3.0e38f) m += t;               // NaN fails the compares
     }
-    float dxq[U], dyq[U];
+    float vq[U], dxq[U], dyq[U];
+    int nxt = col0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const size_t p = col0 + (size_t)min(u, i1 - i0 - 1) * f.ny;
-        dxq[u] = __ldg(Dx + p);
-        dyq[u] = __ldg(Dy + p);
+        vq[u] = __ldg(I + nxt);
+        dxq[u] = __ldg(Dx + nxt);
+        dyq[u] = __ldg(Dy + nxt);
+        nxt = min(nxt + f.ny, last);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m += __shfl_xor_sync(FULL_MASK, m, d);
@@ -64,11 +66,11 @@ splat_tile_kernel(const float* __restrict__ I, const float* __restrict__ Dx, con
     for (int w = 0; w < TILE_COLS / 32; ++w) m += wsum[w];
     // twice the mean = 1.x * 2^e sets a power-of-two unit 2^(e - 19) (the scaling itself is exact); rays below
     // 2^(e+1) convert to less than 2^20 units.  (Mean below 2^-107: no fixed-point path, every ray goes the long way.)
-    m = 2.f * m / (float)((i1 - i0) * min(TILE_COLS, f.ny - blockIdx.x * TILE_COLS));
+    m = 2.f * m / (float)(4 * min(TILE_COLS, f.ny - blockIdx.x * TILE_COLS));
     const unsigned mexp = __float_as_uint(m) >> 23;
     const bool fixed_ok = mexp >= 20u && mexp < 254u;
     const float scale = __uint_as_float((273u - mexp) << 23), inv_scale = __uint_as_float((mexp - 19u) << 23);
-    const unsigned vmax_bits = fixed_ok ? (mexp + 1u) << 23 : 0u;   // 0 <= v < 2^(e+1) as one unsigned compare
+    const unsigned vmax_bits = fixed_ok && live ? (mexp + 1u) << 23 : 0u;   // 0 <= v < 2^(e+1) as one unsigned compare
 
     // window of lower cells (tile coordinates) whose four cells are tile cells and image cells (there the plain
     // floor form is the reference's map, splat.cuh: fast_ray)
@@ -89,20 +91,22 @@ splat_tile_kernel(const float* __restrict__ I, const float* __restrict__ Dx, con
         }
     };
 
+    for (int ub = 0; ub < nrows; ub += U) {
 #pragma unroll
-    for (int u = 0; u < TR; ++u) {
-        if (i0 + u >= i1) break;                                  // block-uniform
-        const float dx = dxq[u % U], dy = dyq[u % U];
-        if (u + U < TR) {
-            const size_t p = col0 + (size_t)min(u + U, i1 - i0 - 1) * f.ny;
-            dxq[u % U] = __ldg(Dx + p);
-            dyq[u % U] = __ldg(Dy + p);
-        }
-        const bool fast = lean_deposit<SC, SR, false>(win_s, trow0 + u, tcol, win_r, win_c, v[u], dx, dy, scale, live ? vmax_bits : 0u);
-        if (!fast && live) {
-            const unsigned slot = atomicAdd(qcount, 1u);
-            if (slot < (unsigned)MQ) queue[slot] = make_uint4(((unsigned)tid << 8) | (unsigned)u, __float_as_uint(v[u]), __float_as_uint(dx), __float_as_uint(dy));
-            else long_way(i0 + u, j, v[u], dx, dy);
+        for (int s = 0; s < U; ++s) {
+            const int u = ub + s;
+            if (u >= nrows) break;                                // block-uniform
+            const float v = vq[s], dx = dxq[s], dy = dyq[s];
+            vq[s] = __ldg(I + nxt);                               // row u + U (clamped: the last rows are fetched again)
+            dxq[s] = __ldg(Dx + nxt);
+            dyq[s] = __ldg(Dy + nxt);
+            nxt = min(nxt + f.ny, last);
+            const bool fast = lean_deposit<SC, SR, false>(win_s, trow0 + u, tcol, win_r, win_c, v, dx, dy, scale, vmax_bits);
+            if (!fast && live) {
+                const unsigned slot = atomicAdd(qcount, 1u);
+                if (slot < (unsigned)MQ) queue[slot] = make_uint4(((unsigned)tid << 8) | (unsigned)u, __float_as_uint(v), __float_as_uint(dx), __float_as_uint(dy));
+                else long_way(i0 + u, j, v, dx, dy);
+            }
         }
     }
     __syncthreads();

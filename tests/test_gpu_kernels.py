@@ -111,7 +111,7 @@ def test_splat_large_conservation(abi):
         outs.append(out)
         assert abs(out.double().sum().item() / I.double().sum().item() - 1) < 1e-6
     assert rel_l2(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6
-    assert rel_l2(outs[2].cpu().numpy(), outs[0].cpu().numpy()) < 2e-6
+    assert rel_l2(outs[2].cpu().numpy(), outs[0].cpu().numpy()) < 5e-6      # unit = 2^-18 of these rays, weights floored
     # negative and very unequal intensities, `out +=` on a non-zero image: the tile variant against plain REDs
     I2 = (I * (1.0 + 50.0 * (torch.rand((n, n), device="cuda") > 0.999))).contiguous()
     I2[100:110, 200:260] = -3.0

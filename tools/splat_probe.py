@@ -12,8 +12,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 variants = [int(v) for v in sys.argv[2:]] or [2, 3]
 torch.manual_seed(0)
 I = torch.rand((n, n), device="cuda") + 0.5
-Dx = 3.0 * torch.randn((n, n), device="cuda")
-Dy = 3.0 * torch.randn((n, n), device="cuda")
+if os.environ.get("SPLAT_FIELD", "caps") == "random":
+    Dx = 3.0 * torch.randn((n, n), device="cuda")
+    Dy = 3.0 * torch.randn((n, n), device="cuda")
+else:
+    # membrane-like: gradient of a lattice of spherical caps (period 37 px), mean |D| ~ 1.5 px, torn at the cap edges
+    x = torch.arange(n, device="cuda", dtype=torch.float32) / 37.0
+    fx, fy = (x % 1.0 - 0.5)[:, None], ((x * 1.07) % 1.0 - 0.5)[None, :]
+    t = torch.sqrt(torch.clamp(0.2 - fx * fx - fy * fy, min=0.0))
+    Dx, Dy = torch.gradient(t)
+    s = 1.5 / float(Dx.abs().mean())
+    Dx = (s * Dx).contiguous(); Dy = (s * Dy).contiguous()
+    del t
+print("mean |D|", float(Dx.abs().mean()), float(Dy.abs().mean()), "max", float(Dx.abs().max()))
 out = torch.zeros((n, n), device="cuda")
 for v in variants:
     out.zero_()
