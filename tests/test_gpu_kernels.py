@@ -366,6 +366,40 @@ def test_tile_hop_kernel_matches_direct_kernel(abi, shape, tile_config):
     assert int(flag.item()) & abi.FLAG_NONFINITE
 
 
+def _misaligned(shape, fill=0.0):
+    """A contiguous [nx, ny] float32 view that starts 4 bytes into its allocation (no 16-byte alignment)."""
+    buf = torch.full((shape[0] * shape[1] + 1,), fill, device="cuda", dtype=torch.float32)
+    return buf[1:].view(shape)
+
+
+def test_tile_kernels_with_unaligned_images(abi):
+    """Images that are not 16-byte aligned and a pitch that is not a multiple of 4: the vector flush / zero-fill
+    paths must step aside (lean hop kernel and tile splat against the direct kernels)."""
+    rng = np.random.default_rng(11)
+    for shape in ((300, 520), (300, 523)):
+        x = np.linspace(0, 9, shape[0])[:, None]; y = np.linspace(0, 9, shape[1])[None, :]
+        caps = np.sqrt(np.maximum(0.0, 0.2 - (np.mod(x, 1.0) - 0.5) ** 2 - (np.mod(y, 1.0) - 0.5) ** 2))
+        t_mem = dev((6e-4 * caps).astype(np.float32))
+        E, pix, M, d3 = 52.0, 2.9256, 1.0254, 3.6
+        g3m, a3m = _layer_coeffs([5.97e-7], [5.37e-9], E, d3, M, pix)
+        i0 = 7500.0
+        ref = torch.zeros(shape, device="cuda")
+        abi.refract_layers(None, i0, [(t_mem, g3m[0], 0.0, a3m[0])], ref)
+        out = _misaligned(shape)
+        junk = [_misaligned(shape, 3.0) for _ in range(3)]
+        abi.refract_layers(None, i0, [(t_mem, g3m[0], 0.0, a3m[0])], out, zero_fill=junk, intensity_scale=i0)
+        assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 3e-6
+        assert not any(j.any() for j in junk)
+        # stand-alone splat, variant 3 into an unaligned image
+        I = dev(rng.uniform(0.5, 2.0, shape).astype(np.float32))
+        Dx = dev((2.5 * np.sin(1.3 * x + 0.4 * y)).astype(np.float32) * np.ones(shape, dtype=np.float32))
+        Dy = dev((2.5 * np.cos(0.7 * x + 1.1 * y)).astype(np.float32) * np.ones(shape, dtype=np.float32))
+        a = torch.zeros(shape, device="cuda"); b = _misaligned(shape)
+        abi.splat(I, Dx, Dy, a, margin=15, variant=0)
+        abi.splat(I, Dx, Dy, b, margin=15, variant=3)
+        assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 5e-6
+
+
 @pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
 def test_tile_hop_kernel_cannot_overflow(abi, tile_config):
     """Every ray of a tile focused into ONE cell (a lens): the fixed-point tile holds it (rays per tile x
