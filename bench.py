@@ -16,6 +16,10 @@ One step = one 20-position job.  `value` is measured with all inputs resident in
 membrane map copied back as main.py:99 does).  N > 1: one process per GPU (torchrun), each rank
 its own 20 positions, no data-path collective (positions are independent) -> weak scaling.
 
+At N = 1 the line also carries `splat`: BASELINE.json's second figure, the stand-alone refraction splat
+(`paresis_splat`, 16 algorithmic bytes per study pixel) timed live on a membrane's displacement field at 2048^2 and
+8192^2, direct REDs (variant 2) next to the shared-memory tile kernel (variant 3), as GB/s and fraction of the HBM peak.
+
 `--impl reference` times the CPU oracle port of the same path (oracle/, fp64 numpy + C) on the
 host cores, one process per core, on a bounded sample of the same workload.
 """
