@@ -35,4 +35,9 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b.ravel())
-    return float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
+    val = float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
+    if os.environ.get("PARESIS_REPORT_L2"):       # parity report: every measured distance, with its call site
+        fr = sys._getframe(1)
+        with open(os.environ["PARESIS_REPORT_L2"], "a") as fh:
+            fh.write("%s:%d %s %.3e\n" % (os.path.basename(fr.f_code.co_filename), fr.f_lineno, fr.f_code.co_name, val))
+    return val

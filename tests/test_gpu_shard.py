@@ -46,8 +46,10 @@ def test_world1_matches_single_call(noise):
                 # at most a handful of draws sitting exactly on a decision boundary may move
                 assert np.mean(a != b) < 2e-3 and rel_l2(a, b) < 1e-3, k
             else:
-                assert rel_l2(a, b) < 1e-6, k
-        assert np.allclose(got["mean_energy"], ref["mean_energy"], rtol=1e-9)
+                # (the single call sends the energies of a bin through paresis_refract_group, the sharded one
+                # energy by energy through the lean hop kernel: two fixed-point roundings of the same deposits)
+                assert rel_l2(a, b) < 3e-6, k
+        assert np.allclose(got["mean_energy"], ref["mean_energy"], rtol=1e-7)     # fp32 partial sums of the reference beam: the miss list is drained in arrival order
 
 
 def _rank_main(rank, world, port, q):
