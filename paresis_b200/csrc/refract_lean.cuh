@@ -30,6 +30,12 @@ __device__ __forceinline__ void reds4(unsigned addr, unsigned w0, unsigned w1, u
         : "memory");
 }
 
+// (a * b + 2^31) >> 32: the product of a fixed-point value and a 0.32 fraction, rounded to nearest (one IMAD.WIDE;
+// a plain multiply-high would floor, i.e. move 2^-20 of every ray towards its lower cell)
+__device__ __forceinline__ unsigned mulhi_rn(unsigned a, unsigned b) {
+    return (unsigned)(((unsigned long long)a * b + 0x80000000ull) >> 32);
+}
+
 // Fast path of one ray; false = the ray has to go the long way.  The window of lower cells whose four cells lie
 // inside the tile and strictly inside the image is nr x nc cells from `win_s` (shared address of its first cell);
 // (trow, tcol): the source pixel in window coordinates.
@@ -47,9 +53,9 @@ __device__ __forceinline__ bool lean_deposit(unsigned win_s, int trow, int tcol,
     // two beams of a pixel interleave instead of waiting on each other
     const unsigned fx = __float_as_uint(__fadd_rz(dx, (M + 1.f) - tx)) << 9, fy = __float_as_uint(__fadd_rz(dy, (M + 1.f) - ty)) << 9;
     const unsigned V = __float2uint_rn(v * scale);
-    const unsigned V1 = __umulhi(V, fx), V0 = V - V1;
-    const unsigned w1 = __umulhi(V0, fy), w0 = V0 - w1;
-    const unsigned w3 = __umulhi(V1, fy), w2 = V1 - w3;
+    const unsigned V1 = mulhi_rn(V, fx), V0 = V - V1;
+    const unsigned w1 = mulhi_rn(V0, fy), w0 = V0 - w1;
+    const unsigned w3 = mulhi_rn(V1, fy), w2 = V1 - w3;
     const unsigned addr = win_s + (unsigned)kx * (SC * 4u) + (unsigned)ky * 4u;
     if (fast) {
         reds4(addr, w0, w1, w2, w3, SC * 4u);
