@@ -366,6 +366,37 @@ def test_tile_hop_kernel_matches_direct_kernel(abi, shape, tile_config):
     assert int(flag.item()) & abi.FLAG_NONFINITE
 
 
+@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+@pytest.mark.parametrize("n_extra", [2, 3])
+def test_tile_hop_kernels_with_three_and_four_layers(abi, tile_config, n_extra):
+    """Membrane + 2 or 3 sample materials (the multi-material phantoms of createSampGeom.py:110-260): the tile
+    kernels' 3- and 4-layer instantiations, one and two beams, against the direct kernel."""
+    shape = (300, 600)
+    rng = np.random.default_rng(3)
+    x = np.linspace(0, 9, shape[0])[:, None]; y = np.linspace(0, 9, shape[1])[None, :]
+    caps = np.sqrt(np.maximum(0.0, 0.2 - (np.mod(x, 1.0) - 0.5) ** 2 - (np.mod(y, 1.0) - 0.5) ** 2))
+    E, pix, M, d3 = 52.0, 2.9256, 1.0254, 3.6
+    g3m, _ = _layer_coeffs([5.97e-7], [5.37e-9], E, d3, M, pix)
+    layers = [(dev((6e-4 * caps).astype(np.float32)), g3m[0], g3m[0], 0.0)]
+    for k in range(n_extra):
+        t = (7e-4 * np.exp(-((x - 3.0 - 1.5 * k) ** 2 + (y - 4.0 - 0.7 * k) ** 2) / (1.0 + 0.5 * k))).astype(np.float32)
+        g, a = _layer_coeffs([9.52e-8 * (1 + 0.4 * k)], [4.4e-11 * (1 + k)], E, d3, M, pix)
+        layers.append((dev(t), g[0], 0.0, a[0]))
+    i0 = 7500.0
+    i_in = dev((i0 * (0.6 + 0.8 * rng.random(shape))).astype(np.float32))
+    ref_s = torch.zeros(shape, device="cuda"); ref_r = torch.zeros(shape, device="cuda")
+    abi.refract_layers(i_in, 0.0, layers, ref_s, ref_r)
+    out_s = torch.zeros(shape, device="cuda"); out_r = torch.zeros(shape, device="cuda")
+    abi.refract_layers(i_in, 0.0, layers, out_s, out_r, intensity_scale=i0)
+    assert rel_l2(out_s.cpu().numpy(), ref_s.cpu().numpy()) < 3e-6
+    assert rel_l2(out_r.cpu().numpy(), ref_r.cpu().numpy()) < 3e-6
+    one_ref = torch.zeros(shape, device="cuda"); one = torch.zeros(shape, device="cuda")
+    single = [(t, g, 0.0, a) for (t, g, _, a) in layers]
+    abi.refract_layers(None, i0, single, one_ref)
+    abi.refract_layers(None, i0, single, one, intensity_scale=i0)
+    assert rel_l2(one.cpu().numpy(), one_ref.cpu().numpy()) < 3e-6
+
+
 def _misaligned(shape, fill=0.0):
     """A contiguous [nx, ny] float32 view that starts 4 bytes into its allocation (no 16-byte alignment)."""
     buf = torch.full((shape[0] * shape[1] + 1,), fill, device="cuda", dtype=torch.float32)
