@@ -1,20 +1,24 @@
-// Lean form of the fixed-point tile hop (refract_tile.cuh; same contract, same tile layout and flush).
-// The tile kernel is bound by instruction issue, so this one spends fewer instructions per ray:
+// Lean form of the fixed-point tile hop (refract_tile.cuh; same contract, same tile layout) -- the production hop.
+// It spends 20-30 % fewer instructions per ray than the first tile kernel (what that bought, and what bounds the hops
+// instead, is in DESIGN.md section 3 and profiles/r01_summary.md):
 //
 //  * floor and fraction of a displacement come from magic-number adds on the FMA pipe (see lean_deposit) instead of
 //    FRND / F2I on the quarter-rate pipe; NaN, Inf and huge displacements fail the tile-window test by themselves.
 //  * the ray is converted to fixed point once (V = round(v * S)) and split between its four cells with integer
-//    multiply-high: V1 = V * fx >> 32, V0 = V - V1, ... -- the four parts add up to V exactly, whatever the order.
+//    multiply-high, rounded to nearest: V1 = (V * fx + 2^31) >> 32, V0 = V - V1, ... -- the four parts add up to V
+//    exactly, whatever the order.
+//  * both beams of a pixel are computed before any branch, so that their dependent chains interleave.
 //  * row neighbours come from L1 (two more loads off the address of the row fetched one step earlier) instead of two
 //    shuffles, two selects and a halo column per map.
-//  * rays that cannot take the tile (outside the halo, too bright, negative, not finite) are not handled where they
+//  * rays that cannot take the tile (outside its window, too bright, negative, not finite) are not handled where they
 //    occur -- that made ~30 % of the warp-steps of a membrane walk through the long fp32 path for one or two lanes --
 //    but pushed on a small shared-memory list and deposited densely once the block is through its rows.
 //  * the first and last warp of an image row and the first / last block of rows run a second copy of the loop
 //    with clamped loads and the edge rules of np.gradient; the interior copy has neither.
+//  * the tile is zeroed and flushed only over the rows this block can reach, by a flat walk over its quads.
 //
-// The bilinear fractions are thereby truncated to 23 bits and the weights to one fixed-point unit; results agree
-// with the first tile kernel to ~1e-7 relative L2.
+// The bilinear fractions are truncated to 23 bits and the weights rounded to one fixed-point unit; end-to-end images
+// sit at the same distance from the reference as with the first tile kernel (profiles/r01_parity_distances.txt).
 #pragma once
 #include "refract_tile.cuh"
 
@@ -30,7 +34,7 @@ __device__ __forceinline__ void reds4(unsigned addr, unsigned w0, unsigned w1, u
         : "memory");
 }
 
-// (a * b + 2^31) >> 32: the product of a fixed-point value and a 0.32 fraction, rounded to nearest (one IMAD.WIDE;
+// (a * b + 2^31) >> 32: the product of a fixed-point value and a 0.32 fraction, rounded to nearest (one IMAD.HI with a 64-bit addend;
 // a plain multiply-high would floor, i.e. move 2^-20 of every ray towards its lower cell)
 __device__ __forceinline__ unsigned mulhi_rn(unsigned a, unsigned b) {
     return (unsigned)(((unsigned long long)a * b + 0x80000000ull) >> 32);
