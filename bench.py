@@ -399,7 +399,7 @@ def splat_roofline(abi, geometry, exp, torch, flush, peak):
         del dxp, dyp, phi, geom
         inten = (inten * (0.7 + 0.6 * torch.rand((n, n), device="cuda"))).contiguous()
         res = {"mean_abs_displacement_px": float((dx.abs().mean() + dy.abs().mean()).item() / 2)}
-        for variant, label in ((2, "direct_red"), (3, "smem_tiles")):
+        for variant, label in ((2, "direct_red"), (3, "smem_tiles"), (4, "owner_strips"), (5, "owner_strips_accumulate")):
             for _ in range(3):
                 abi.splat(inten, dx, dy, tmp, margin=15, variant=variant)
             times = []

@@ -49,4 +49,8 @@ int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_
 // Stand-alone splat through fixed-point shared-memory tiles (splat_tile.cu): variant 3 of paresis_splat.
 int launch_splat_tile(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, cudaStream_t s);
 
+// Stand-alone splat as an owner-computes rolling-strip kernel (splat_strip.cu): variants 4 (out = ...) and 5 (out += ...).
+int launch_splat_strip(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, bool accumulate,
+                       cudaStream_t s);
+
 }  // namespace paresis

@@ -48,11 +48,12 @@ __device__ __forceinline__ unsigned mulhi_rn(unsigned a, unsigned b) {
 // in ONE rounding, always below 2: its mantissa is the bilinear fraction in 0.23 fixed point.
 template <int SC, int SR, bool TWIN>
 __device__ __forceinline__ bool lean_deposit(unsigned win_s, int trow, int tcol, unsigned nr, unsigned nc, float v, float dx, float dy,
-                                             float scale, unsigned vmax_bits) {
+                                             float scale, unsigned vmin_bits, unsigned vspan) {
     constexpr float M = 12582912.f;
     const float tx = __fadd_rd(dx, M), ty = __fadd_rd(dy, M);
     const int kx = (int)(__float_as_uint(tx) - 0x4B400000u) + trow, ky = (int)(__float_as_uint(ty) - 0x4B400000u) + tcol;
-    const bool fast = (unsigned)kx < nr && (unsigned)ky < nc && __float_as_uint(v) < vmax_bits;
+    // vmin <= v < vmax as one unsigned compare on the bit pattern (negative, NaN and zero patterns fall outside)
+    const bool fast = (unsigned)kx < nr && (unsigned)ky < nc && (__float_as_uint(v) - vmin_bits) < vspan;
     // branch-free up to the atomics (a lane that fails computes garbage it does not use), so that the chains of the
     // two beams of a pixel interleave instead of waiting on each other
     const unsigned fx = __float_as_uint(__fadd_rz(dx, (M + 1.f) - tx)) << 9, fy = __float_as_uint(__fadd_rz(dy, (M + 1.f) - ty)) << 9;
@@ -146,6 +147,8 @@ refract_lean_kernel(const RefractArgs<float> a) {
     // rays below vmax convert to less than 2^32 / (TR * 256) - 4 units: a whole tile cannot overflow one cell
     const float fix_scale = (float)(1u << FIX_BITS) / a.intensity_scale;
     const unsigned vmax_bits = __float_as_uint(a.intensity_scale * (float)((unsigned)((1ull << 32) / (TR * TILE_COLS)) - 8u) / (float)(1u << FIX_BITS));
+    // rays below 2^9 units (2^-10 of the intensity scale) would be quantised to worse than 1e-3: they take the fp32 list
+    const unsigned vmin_bits = __float_as_uint(a.intensity_scale * (1.0f / 1024.0f));
     const float neg_log2e = -1.4426950408889634f;
     // zero-fill of the buffers the next kernel scatters into: this block's rows x 256 columns, with 128-bit stores
     // when the layout allows it, else pixel by pixel in the row loop (the host fills unused slots with a used pointer)
@@ -183,6 +186,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
 
     // a ray that cannot take the tile: remember it (16 bytes), or deposit it now if the list is full
     auto miss = [&](unsigned flags, int i, float v, float dx, float dy) {
+        if (v == 0.f) return;                          // nothing to deposit (and not worth a list entry)
         const unsigned slot = atomicAdd(qcount, 1u);
         if (slot < (unsigned)MQ) {
             queue[slot] = make_uint4(flags | ((unsigned)tid << 8) | (unsigned)(i - i0), __float_as_uint(v), __float_as_uint(dx),
@@ -198,16 +202,16 @@ refract_lean_kernel(const RefractArgs<float> a) {
     // the ray(s) of one source pixel: into the tile(s), or on the list.  `dead` = 0, or ~0u for a lane outside
     // the image (it must run the warp vote, and deposits nothing)
     auto emit = [&](int i, int trow, float vo, float vin, float dxo, float dyo, float dxr, float dyr, unsigned dead) {
-        const unsigned vmax = vmax_bits & ~dead;      // a dead lane fails "v < vmax" ...
+        const unsigned vspan = (vmax_bits - vmin_bits) & ~dead;      // a dead lane fails the range test ...
         if (DUAL) {
             // outside the sample the two beams are the same ray: form it once, deposit it twice
             const bool same = dxo == dxr && dyo == dyr && vo == vin;
             if (__all_sync(FULL_MASK, same)) {
-                if (lean_deposit<SC, SR, true>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmax)) ref_sum += vo;
+                if (lean_deposit<SC, SR, true>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmin_bits, vspan)) ref_sum += vo;
                 else if (!dead) miss(MISS_TWIN, i, vo, dxo, dyo);     // ... and is not a miss either
             } else {
-                const bool fo = lean_deposit<SC, SR, false>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmax);
-                const bool fr = lean_deposit<SC, SR, false>(win_s + SR * SC * 4u, trow, tcol, win_r, win_c, vin, dxr, dyr, fix_scale, vmax);
+                const bool fo = lean_deposit<SC, SR, false>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmin_bits, vspan);
+                const bool fr = lean_deposit<SC, SR, false>(win_s + SR * SC * 4u, trow, tcol, win_r, win_c, vin, dxr, dyr, fix_scale, vmin_bits, vspan);
                 if (fr) ref_sum += vin;
                 if (!(fo && fr) && !dead) {
                     if (!fo) miss(0u, i, vo, dxo, dyo);
@@ -215,7 +219,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
                 }
             }
         } else {
-            if (!lean_deposit<SC, SR, false>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmax) && !dead) miss(0u, i, vo, dxo, dyo);
+            if (!lean_deposit<SC, SR, false>(win_s, trow, tcol, win_r, win_c, vo, dxo, dyo, fix_scale, vmin_bits, vspan) && !dead) miss(0u, i, vo, dxo, dyo);
         }
     };
 

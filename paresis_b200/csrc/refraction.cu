@@ -279,6 +279,8 @@ extern "C" int paresis_splat(const float* intensity, const float* dx, const floa
         case 1: splat_kernel<1><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
         case 2: splat_kernel<2><<<grid, BLOCK_THREADS, 0, s>>>(intensity, dx, dy, out, f, rows, flag); break;
         case 3: return launch_splat_tile(intensity, dx, dy, out, f, flag, s);
+        case 4: return launch_splat_strip(intensity, dx, dy, out, f, flag, false, s);    // out  = splat (owner computes, plain stores)
+        case 5: return launch_splat_strip(intensity, dx, dy, out, f, flag, true, s);     // out += splat (owner adds its rows)
         default: set_last_error("paresis_splat: unknown variant %d", variant); return PARESIS_ERR_ARG;
     }
     PARESIS_LAUNCH_CHECK("splat_kernel");

@@ -101,7 +101,7 @@ splat_tile_kernel(const float* __restrict__ I, const float* __restrict__ Dx, con
             dxq[s] = __ldg(Dx + nxt);
             dyq[s] = __ldg(Dy + nxt);
             nxt = min(nxt + f.ny, last);
-            const bool fast = lean_deposit<SC, SR, false>(win_s, trow0 + u, tcol, win_r, win_c, v, dx, dy, scale, vmax_bits);
+            const bool fast = lean_deposit<SC, SR, false>(win_s, trow0 + u, tcol, win_r, win_c, v, dx, dy, scale, 0u, vmax_bits);
             if (!fast && live) {
                 const unsigned slot = atomicAdd(qcount, 1u);
                 if (slot < (unsigned)MQ) queue[slot] = make_uint4(((unsigned)tid << 8) | (unsigned)u, __float_as_uint(v), __float_as_uint(dx), __float_as_uint(dy));
