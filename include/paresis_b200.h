@@ -115,8 +115,15 @@ typedef struct {
     double* zero_scalar;
     double* sum_ref;
     float intensity_scale;   /* > 0: the nominal beam intensity (e.g. I0 * flux).  Enables the shared-memory tile
-                                kernel, which accumulates in 32-bit fixed point with a unit of intensity_scale / 2^19;
-                                rays brighter than 2 x intensity_scale, or negative, still take the fp32 path. */
+                                kernels, which accumulate in 32-bit fixed point with a unit of intensity_scale / 2^19
+                                (2^21 .. 2^22 in the strip kernels); rays brighter than 2 x intensity_scale, dimmer than
+                                2^9 units, or negative, still take the fp32 path. */
+    int mode;                /* 0: out += result, source-owner tiles + REDs (round-1 kernels; honours every field above);
+                                1: out  = result  (fastRefraction's own contract: it scatters into fresh zeros,
+                                   refractionFileNumba2.py:70,77) -- owner-computes rolling strips, plain stores;
+                                2: out += result, owner-computes rolling strips (the owner adds its finished rows).
+                                Modes 1 / 2 need intensity_scale and ignore zero_fill / clear_input / zero_scalar. */
+    int reach;               /* modes 1 / 2, single beam: 8 or 12 = pixels a ray may move and still take the tiles */
 } paresis_refract_extras;
 
 int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform,
@@ -124,6 +131,24 @@ int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform
                               float* out_obj, float* out_ref, float* dx_pad, float* dy_pad,
                               int nx, int ny, int margin, int* flag,
                               const paresis_refract_extras* extras_host, paresis_stream stream);
+
+/* The strip hop (modes 1 / 2 above) for up to PARESIS_MAX_HOP_BATCH membrane positions in ONE launch: the items share
+ * the layer coefficients (layers_host[m].grad_obj / grad_ref / atten; its thickness pointers are ignored) and differ in
+ * their images.  Experiment.py:463-474 for each item.  `work`: scratch of paresis_refract_hop_work_bytes() bytes for the
+ * rays that cannot take the tiles (NULL: taken from the stream-ordered pool for the duration of the call). */
+#define PARESIS_MAX_HOP_BATCH 8
+typedef struct {
+    const float* intensity_in;                      /* NULL: uniform `intensity_uniform` */
+    const float* thickness[PARESIS_MAX_LAYERS];
+    float* out_obj;
+    float* out_ref;                                 /* NULL: single beam */
+    double* sum_ref;                                /* *sum_ref += what the reference beam deposits inside the image; may be NULL */
+} paresis_hop_item;
+
+size_t paresis_refract_hop_work_bytes(int nx, int ny, int n_layers, int n_items, int dual, int has_intensity_map, int reach);
+int paresis_refract_hop_batch(const paresis_hop_item* items_host, int n_items, const paresis_layer* layers_host, int n_layers,
+                              float intensity_uniform, float intensity_scale, int accumulate, int reach, int nx, int ny,
+                              void* work, size_t work_bytes, int* flag, paresis_stream stream);
 
 /* The object hop (sample + reference beams, as paresis_refract_layers with out_ref) of up to
  * PARESIS_MAX_GROUP energies of ONE detector bin in a single pass: inside a bin every energy repeats the hop

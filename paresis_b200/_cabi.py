@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libparesis_b200.so")
 OK = 0
 FLAG_NONFINITE = 1
 MAX_LAYERS = 4
+MAX_HOP_BATCH = 8      # membrane positions that can share one strip-hop launch (paresis_refract_hop_batch)
 MAX_GROUP = 4          # energies of a detector bin that can share one object hop (paresis_refract_group)
 REFRACTION_MARGIN = 15   # refractionFileNumba2.py:50
 REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
@@ -29,7 +30,7 @@ EXPORTS = (
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
     "paresis_two_sphere_phantom", "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
-    "paresis_refract_group", "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
+    "paresis_refract_group", "paresis_refract_hop_batch", "paresis_refract_hop_work_bytes", "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
 
@@ -92,7 +93,12 @@ class Membrane(ctypes.Structure):
 
 class RefractExtras(ctypes.Structure):
     _fields_ = [("zero_fill", ctypes.c_void_p * 3), ("clear_input", ctypes.c_int), ("zero_scalar", ctypes.c_void_p),
-                ("sum_ref", ctypes.c_void_p), ("intensity_scale", ctypes.c_float)]
+                ("sum_ref", ctypes.c_void_p), ("intensity_scale", ctypes.c_float), ("mode", ctypes.c_int), ("reach", ctypes.c_int)]
+
+
+class HopItem(ctypes.Structure):
+    _fields_ = [("intensity_in", ctypes.c_void_p), ("thickness", ctypes.c_void_p * MAX_LAYERS), ("out_obj", ctypes.c_void_p),
+                ("out_ref", ctypes.c_void_p), ("sum_ref", ctypes.c_void_p)]
 
 
 class C32(ctypes.Structure):
@@ -142,6 +148,7 @@ def _load():
         "paresis_df_split": [vp, cf, vp, cf, vp, vp, vp, sz, vp],
         "paresis_df_scatter": [vp, vp, vp, ci, ci, vp],
         "paresis_refract_group": [ctypes.POINTER(GroupEnergy), ci, vp, vp, ci, ci, vp, vp],
+        "paresis_refract_hop_batch": [ctypes.POINTER(HopItem), ci, ctypes.POINTER(Layer), ci, cf, cf, ci, ci, ci, ci, vp, sz, vp, vp],
         "paresis_transfer_lane_create": [ctypes.POINTER(vp)],
         "paresis_transfer_lane_destroy": [vp],
         "paresis_transfer_d2h": [vp, vp, vp, sz, vp],
@@ -159,6 +166,8 @@ def _load():
     lib.paresis_detect_work_floats.restype = sz
     lib.paresis_fresnel_plan_bytes.argtypes = [vp]
     lib.paresis_fresnel_plan_bytes.restype = sz
+    lib.paresis_refract_hop_work_bytes.argtypes = [ci, ci, ci, ci, ci, ci, ci]
+    lib.paresis_refract_hop_work_bytes.restype = sz
     lib.paresis_raster_work_bytes.argtypes = [ci, ci, ci, ci]
     lib.paresis_raster_work_bytes.restype = sz
     return lib
@@ -288,9 +297,10 @@ def refract_phi(intensity, phi, out, distance, energy_kev, magnification, pixel_
 
 def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=None, margin=REFRACTION_MARGIN, flag=None,
                    dx_pad=None, dy_pad=None, zero_fill=(), clear_input=False, zero_scalar=None, sum_ref=None,
-                   intensity_scale=0.0):
+                   intensity_scale=0.0, mode=0, reach=0):
     """layers: list of (thickness tensor, grad_obj, grad_ref, atten); the keyword extras are
-    paresis_refract_extras (zero_fill: up to 3 float32 images; zero_scalar / sum_ref: float64 scalars)."""
+    paresis_refract_extras (zero_fill: up to 3 float32 images; zero_scalar / sum_ref: float64 scalars;
+    mode 0: out += through the round-1 kernels, 1: out = / 2: out += through the owner-computes strip kernels)."""
     n = len(layers)
     arr = (Layer * n)()
     for k, (t, go, gr, at) in enumerate(layers):
@@ -307,11 +317,39 @@ def refract_layers(intensity_in, intensity_uniform, layers, out_obj, out_ref=Non
     extras.zero_scalar = zero_scalar.data_ptr() if zero_scalar is not None else None
     extras.sum_ref = sum_ref.data_ptr() if sum_ref is not None else None
     extras.intensity_scale = float(intensity_scale)
+    extras.mode, extras.reach = int(mode), int(reach)
     _check(_timed(label, lambda: lib.paresis_refract_layers_ex(
         _ptr(intensity_in, torch.float32), float(intensity_uniform), arr, n, _ptr(out_obj, torch.float32),
         _ptr(out_ref, torch.float32), _ptr(dx_pad, torch.float32), _ptr(dy_pad, torch.float32), nx, ny, margin,
         _ptr(flag, torch.int32), ctypes.byref(extras), _stream())), "paresis_refract_layers_ex")
     _count()
+
+
+def refract_hop_batch(items, coeffs, intensity_uniform, intensity_scale, accumulate=False, reach=12, work=None, flag=None):
+    """paresis_refract_hop_batch.  items: list of dicts {intensity_in (tensor | None), thickness (list of tensors),
+    out_obj, out_ref (tensor | None), sum_ref (float64 tensor | None)}; coeffs: list of (grad_obj, grad_ref, atten)."""
+    n = len(items)
+    arr = (HopItem * n)()
+
+    def addr(t, dtype):
+        _ptr(t, dtype)
+        return t.data_ptr() if t is not None else None
+
+    for k, it in enumerate(items):
+        arr[k].intensity_in = addr(it.get("intensity_in"), torch.float32)
+        for m, t in enumerate(it["thickness"]):
+            arr[k].thickness[m] = addr(t, torch.float32)
+        arr[k].out_obj = addr(it["out_obj"], torch.float32)
+        arr[k].out_ref = addr(it.get("out_ref"), torch.float32)
+        arr[k].sum_ref = addr(it.get("sum_ref"), torch.float64)
+    lay = (Layer * len(coeffs))()
+    for m, (go, gr, at) in enumerate(coeffs):
+        lay[m].grad_obj, lay[m].grad_ref, lay[m].atten = float(go), float(gr), float(at)
+    nx, ny = items[0]["out_obj"].shape
+    _check(lib.paresis_refract_hop_batch(arr, n, lay, len(coeffs), float(intensity_uniform), float(intensity_scale),
+                                         1 if accumulate else 0, int(reach), nx, ny, _ptr(work), work.numel() * work.element_size() if work is not None else 0,
+                                         _ptr(flag, torch.int32), _stream()), "paresis_refract_hop_batch")
+    _count(2)
 
 
 def refract_group(energies, out_obj, out_ref, flag=None):

@@ -359,6 +359,18 @@ extern "C" int paresis_refract_layers_ex(const float* intensity_in, float intens
     a.rows = pick_rows(nx, ny);
     a.flag = flag;
     cudaStream_t s = (cudaStream_t)stream;
+    if (extras && extras->mode != 0) {
+        // owner-computes rolling strips (refract_strip.cu): out = / out += without atomics on the image
+        if (dx_pad) { set_last_error("paresis_refract_layers: the displacement maps come from mode 0 only"); return PARESIS_ERR_ARG; }
+        paresis_hop_item item{};
+        item.intensity_in = intensity_in;
+        for (int m = 0; m < n_layers; ++m) item.thickness[m] = layers_host[m].thickness;
+        item.out_obj = out_obj;
+        item.out_ref = out_ref;
+        item.sum_ref = out_ref ? extras->sum_ref : nullptr;
+        return paresis_refract_hop_batch(&item, 1, layers_host, n_layers, intensity_uniform, extras->intensity_scale, extras->mode == 2,
+                                         extras->reach > 0 ? extras->reach : 12, nx, ny, nullptr, 0, flag, stream);
+    }
     if (extras) {
         // compact the zero-fill list; kernels that test only slot 0 get every slot filled (a repeated store is harmless)
         int nz = 0;

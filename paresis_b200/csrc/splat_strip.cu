@@ -11,23 +11,23 @@
 // carries no intensity scale: every block takes the same one from a fixed 16 x 16 lattice of the intensity image
 // (twice the mean of its finite positive samples, rounded down to a power of two -- the scaling itself is exact), so
 // that all blocks agree on which rays are tile rays.  Rays outside [2^-13, 2) of that scale, like rays that move
-// further than H = 8 pixels or touch the image border, go through make_ray() -- the reference's loop-frame rules --
+// further than H = 12 pixels or touch the image border, go through make_ray() -- the reference's loop-frame rules --
 // in the drain launch.
 #include "strip.cuh"
 
 namespace paresis {
 
-constexpr int SPLAT_H = 8;
+constexpr int SPLAT_H = 12;     // reach of the tile path; on a membrane's field 0.16 % of the rays move further (1.9 % at H = 8)
 
 template <int H, bool ACC>
-__global__ void __launch_bounds__(STRIP_THREADS, 5)
+__global__ void __launch_bounds__(STRIP_BLOCK, 5)
 splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const float* __restrict__ Dy, float* __restrict__ out,
                    Frame f, StripPlan p, uint4* __restrict__ far, unsigned* __restrict__ far_count, bool vec) {
     using S = Strip<H>;
     constexpr int U = STRIP_U;
     extern __shared__ __align__(16) unsigned strip_smem[];
     unsigned* const tile = strip_smem;
-    unsigned* const misc = strip_smem + S::TILE_WORDS;      // [0] list counter, [1] sample count, [2..9] / [10..17] warp partials
+    unsigned* const misc = strip_smem + S::TILE_WORDS;      // [0..7] / [8..15]: warp partials of the scale sample
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int C0 = blockIdx.x * p.oc;
@@ -37,25 +37,24 @@ splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, co
     const bool live = j >= 0 && j < f.ny && tid < p.oc + 2 * H;
     const int jc = min(max(j, 0), f.ny - 1);
     const bool own_col = j >= C0 && j < C0 + oc;
-    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
-    uint4* const slice = far + (size_t)bid * p.far_cap;
+    const unsigned wid = (blockIdx.y * gridDim.x + blockIdx.x) * STRIP_WARPS + (tid >> 5);
+    uint4* const slice = far + (size_t)wid * p.far_cap;
+    unsigned n_far = 0u;
 
     {
         uint4* z = reinterpret_cast<uint4*>(tile);
-        for (int k = tid; k < S::TILE_WORDS / 4; k += STRIP_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) misc[0] = 0u;
+        for (int k = tid; k < S::TILE_WORDS / 4; k += STRIP_BLOCK) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     // the intensity scale: the same 256 samples in every block
-    float m;
     {
         const int si = (int)(((long long)(2 * (tid >> 4) + 1) * f.nx) >> 5), sj = (int)(((long long)(2 * (tid & 15) + 1) * f.ny) >> 5);
-        const float t = __ldg(I + (size_t)si * f.ny + sj);
+        const float t = tid < STRIP_THREADS ? __ldg(I + (size_t)si * f.ny + sj) : 0.f;
         const bool good = t > 0.f && t < 3.0e38f;              // NaN fails the compares
         float sum = good ? t : 0.f;
-        unsigned cnt = __popc(__ballot_sync(FULL_MASK, good));
+        const unsigned cnt = __popc(__ballot_sync(FULL_MASK, good));
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, d);
-        if (lane == 0) { misc[2 + (tid >> 5)] = __float_as_uint(sum); misc[10 + (tid >> 5)] = cnt; }
+        if (lane == 0 && tid < STRIP_THREADS) { misc[tid >> 5] = __float_as_uint(sum); misc[8 + (tid >> 5)] = cnt; }
     }
 
     // source rows of this block and the first U of them
@@ -65,86 +64,82 @@ splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, co
     float vq[U], dxq[U], dyq[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        vq[u] = __ldg(I + pre); dxq[u] = __ldg(Dx + pre); dyq[u] = __ldg(Dy + pre);
+        strip_prefetch(vq[u], I + pre); strip_prefetch(dxq[u], Dx + pre); strip_prefetch(dyq[u], Dy + pre);
         pre = min(pre + f.ny, last_off);
     }
     __syncthreads();
+    float m;
     {
         float sum = 0.f; unsigned cnt = 0u;
 #pragma unroll
-        for (int w = 0; w < STRIP_THREADS / 32; ++w) { sum += __uint_as_float(misc[2 + w]); cnt += misc[10 + w]; }
+        for (int w = 0; w < STRIP_WARPS; ++w) { sum += __uint_as_float(misc[w]); cnt += misc[8 + w]; }
         m = cnt ? 2.f * sum / (float)cnt : 0.f;
     }
-    // 2 * mean = 1.x * 2^e: unit 2^(e - 22), tile rays in [2^(e - 13), 2^(e + 1)) = [2^9, 2^23) units
+    // 2 * mean = 1.x * 2^e: unit 2^(e + 1 - FIX) ... tile rays in [2^9, 2^(FIX+1)) units = [2^(e + 10 - FIX), 2^(e + 1))
     const unsigned mexp = __float_as_uint(m) >> 23;
-    const bool fixed_ok = mexp >= 24u && mexp < 254u;
-    const float scale = __uint_as_float((276u - mexp) << 23), inv_scale = __uint_as_float((mexp - 22u) << 23);
-    const unsigned vmin_bits = (mexp - 13u) << 23, vspan = fixed_ok ? (14u << 23) : 0u;
+    const bool fixed_ok = mexp >= 32u && mexp < 254u;
+    const float scale = __uint_as_float((254u + S::FIX - mexp) << 23), inv_scale = __uint_as_float((mexp - S::FIX) << 23);
+    const unsigned vmin_bits = (mexp + 9u - S::FIX) << 23, vspan = fixed_ok ? ((unsigned)(S::FIX - 8) << 23) : 0u;
 
+    if (tid >= STRIP_THREADS) {                                    // the flushing warp
+        float* const outs[1] = {out};
+        strip_flusher<H, S::W, 1, ACC, false>(tile, outs, R0, R1, C0, oc, f.nx, f.ny, inv_scale, vec);
+        return;
+    }
     const ColWin cw = col_window<H>(j, C0, p.oc, f.ny, live, (unsigned)__cvta_generic_to_shared(tile));
-    int flush_next = R0 - 1;
-    const unsigned long long half = strip_half();
-
     // rows whose deposit window is the full [-H, H-1] and that this block owns as source rows: most of a segment
     const int in_lo = max(R0 + H - 1, H), in_hi = min(R1 - H, f.nx - 1 - H);
-    const unsigned own_mask = own_col ? ~0u : 0u;
+    const unsigned long long half = strip_half(f.nx);
 
-    // the ray of source pixel (i, j): into the tile, or -- if this block owns the pixel -- on the list when no block's tile takes it
+    // the ray of source pixel (i, j): into the tile, or -- if this block owns the pixel and no block's tile takes the ray -- on the list
     auto ray = [&](int i, const RowWin& rw, bool own_row, float v, float dx, float dy) {
-        const bool ok = strip_deposit<S::W, false>(rw, cw, v, dx, dy, scale, vmin_bits, vspan, 0u, half);
-        if (!ok) {
-            if (own_row && own_mask && v != 0.f) {
-                constexpr float M = 12582912.f;
-                const int kx = (int)(__float_as_uint(__fadd_rd(dx, M)) - STRIP_MAGIC), ky = (int)(__float_as_uint(__fadd_rd(dy, M)) - STRIP_MAGIC);
-                if (!(tile_class<H>(i, j, kx, ky, f.nx, f.ny) && (__float_as_uint(v) - vmin_bits) < vspan))
-                    strip_push(slice, misc, 0u, i * f.ny + j, v, dx, dy);
-            }
+        unsigned bx, by;
+        const bool ok = strip_deposit<S::W, false>(rw, cw, v, dx, dy, scale, vmin_bits, vspan, 0u, half, bx, by);
+        // not deposited here although this block owns the source pixel: a tile ray whose cells belong to the neighbours, or one for the list
+        const bool cand = !ok && own_row && own_col && v != 0.f;
+        if (__any_sync(FULL_MASK, cand)) {                          // warp-uniform; rare away from the strip's edges
+            const bool push = cand && !(tile_class<H>(i, j, bx, by, f.nx, f.ny) && (__float_as_uint(v) - vmin_bits) < vspan);
+            strip_push(slice, n_far, push, (unsigned)(i * f.ny + j), v, dx, dy);
         }
     };
 
-    for (int s = s_begin; s < s_end; s += U) {
+    int k = 0;
+    for (int s = s_begin; s < s_end; s += U, ++k) {
+        if (k >= 2) named_sync(BAR_EMPTY, k & 1);               // the slots this chunk deposits into have been flushed
         if (s >= in_lo && s + U - 1 <= in_hi) {                    // block-uniform
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const float v = vq[u], dx = dxq[u], dy = dyq[u];
-                vq[u] = __ldg(I + pre); dxq[u] = __ldg(Dx + pre); dyq[u] = __ldg(Dy + pre);    // row i + U (clamped)
+                ray(s + u, row_window_interior<H>(s + u), true, vq[u], dxq[u], dyq[u]);
+                strip_prefetch(vq[u], I + pre); strip_prefetch(dxq[u], Dx + pre); strip_prefetch(dyq[u], Dy + pre);    // row s + u + U (clamped)
                 pre = min(pre + f.ny, last_off);
-                RowWin rw;
-                rw.sub = STRIP_MAGIC - (unsigned)H; rw.span = 2u * H; rw.slot = (unsigned)(s + u) - STRIP_MAGIC;
-                ray(s + u, rw, true, v, dx, dy);
             }
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = s + u;
                 if (i >= s_end) break;                             // block-uniform
-                const float v = vq[u], dx = dxq[u], dy = dyq[u];
-                vq[u] = __ldg(I + pre); dxq[u] = __ldg(Dx + pre); dyq[u] = __ldg(Dy + pre);
+                ray(i, row_window<H>(i, R0, R1, f.nx), i >= R0 && i < R1, vq[u], dxq[u], dyq[u]);
+                strip_prefetch(vq[u], I + pre); strip_prefetch(dxq[u], Dx + pre); strip_prefetch(dyq[u], Dy + pre);
                 pre = min(pre + f.ny, last_off);
-                ray(i, row_window<H>(i, R0, R1, f.nx), i >= R0 && i < R1, v, dx, dy);
             }
         }
-        __syncthreads();
-        // rows that no later source row can reach are final
-        const int final_row = s + U >= s_end ? R1 - 1 : s + U - 1 - H;
-        while (flush_next <= final_row) {
-            strip_flush<S::W, ACC>(tile, out, flush_next, min(flush_next + 3, final_row), R0, R1, C0, oc, f.ny, inv_scale, vec);
-            flush_next += 4;
-        }
+        named_arrive(BAR_FULL, k & 1);
     }
-    if (tid == 0) far_count[bid] = misc[0];
+    if (lane == 0) far_count[wid] = n_far;
 }
 
-// The listed rays, in fp32, with the reference's loop-frame rules (make_ray).  One block per list slice.
+// The listed rays, in fp32, with the reference's loop-frame rules (make_ray).  One warp per list slice.
 __global__ void __launch_bounds__(128)
-splat_drain_kernel(const uint4* __restrict__ far, const unsigned* __restrict__ far_count, unsigned far_cap, float* __restrict__ out,
-                   Frame f, int* flag) {
-    const unsigned n = far_count[blockIdx.x];
+splat_drain_kernel(const uint4* __restrict__ far, const unsigned* __restrict__ far_count, unsigned far_cap, unsigned n_slices,
+                   float* __restrict__ out, Frame f, int* flag) {
+    const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_slices) return;
+    const unsigned n = far_count[w];
     if (n == 0u) return;
-    const uint4* slice = far + (size_t)blockIdx.x * far_cap;
+    const uint4* slice = far + (size_t)w * far_cap;
     Splatter<0> sp;
     sp.init(out, f.ny, flag);
-    for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+    for (unsigned k = threadIdx.x & 31; k < n; k += 32) {
         const uint4 e = slice[k];
         const int idx = (int)(e.x & FAR_INDEX);
         const int i = idx / f.ny, j = idx - i * f.ny;
@@ -165,21 +160,21 @@ static int launch_variant(const float* I, const float* Dx, const float* Dy, floa
     constexpr int H = SPLAT_H;
     constexpr size_t smem = sizeof(unsigned) * (Strip<H>::TILE_WORDS + 32);
     int slots = 0;
-    int rc = g_splat_slots[ACC ? 1 : 0].get(splat_strip_kernel<H, ACC>, STRIP_THREADS, smem, &slots);
+    int rc = g_splat_slots[ACC ? 1 : 0].get(splat_strip_kernel<H, ACC>, STRIP_BLOCK, smem, &slots);
     if (rc) return rc;
     const StripPlan p = plan_strips(f.nx, f.ny, H, slots);
-    const size_t blocks = (size_t)p.strips * p.segs;
-    const size_t list_bytes = blocks * p.far_cap * sizeof(uint4);
+    const size_t slices = (size_t)p.strips * p.segs * STRIP_WARPS;
+    const size_t list_bytes = slices * p.far_cap * sizeof(uint4);
     void* scratch = nullptr;
-    rc = strip_scratch_alloc(list_bytes + blocks * sizeof(unsigned), &scratch, s);
+    rc = strip_scratch_alloc(list_bytes + slices * sizeof(unsigned), &scratch, s);
     if (rc) return rc;
     uint4* far = reinterpret_cast<uint4*>(scratch);
     unsigned* far_count = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + list_bytes);
     const bool vec = (f.ny & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     dim3 grid(p.strips, p.segs);
-    splat_strip_kernel<H, ACC><<<grid, STRIP_THREADS, smem, s>>>(I, Dx, Dy, out, f, p, far, far_count, vec);
+    splat_strip_kernel<H, ACC><<<grid, STRIP_BLOCK, smem, s>>>(I, Dx, Dy, out, f, p, far, far_count, vec);
     PARESIS_LAUNCH_CHECK("splat_strip_kernel");
-    splat_drain_kernel<<<(unsigned)blocks, 128, 0, s>>>(far, far_count, p.far_cap, out, f, flag);
+    splat_drain_kernel<<<(unsigned)div_up((int)slices, 4), 128, 0, s>>>(far, far_count, p.far_cap, (unsigned)slices, out, f, flag);
     PARESIS_LAUNCH_CHECK("splat_drain_kernel");
     return strip_scratch_free(scratch, s);
 }

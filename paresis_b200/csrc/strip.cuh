@@ -25,53 +25,59 @@
 // No zero-fill pass, no read-modify-write of the image, results independent of the block schedule for tile rays
 // (integer sums); fp32 summation order only matters for the listed rays.
 //
-// Fixed point: unit = 2^-22 of the intensity scale; a cell collects at most (2H+1)^2 rays of < 2^23 units, so it
-// cannot overflow; rays below 2^9 units (2^-13 of the scale) go on the list instead of being quantised coarsely.
+// Fixed point: unit = 2^-FIX of the intensity scale (FIX = 22 for H <= 8, 21 for H = 12); a cell collects at most
+// (2H+1)^2 rays of < 2^(FIX+1) units, so it cannot overflow; rays below 2^9 units go on the list instead of being
+// quantised coarsely.  The list is per WARP (its 32 columns x the segment's rows): appending needs no atomics.
 #pragma once
 #include "splat.cuh"
 
 namespace paresis {
 
-constexpr int STRIP_THREADS = 256;   // source columns per block
+constexpr int STRIP_THREADS = 256;   // source columns per block = depositing threads
+constexpr int STRIP_WARPS = STRIP_THREADS / 32;
+constexpr int STRIP_FLUSH_WARPS = 1;
+constexpr int STRIP_BLOCK = STRIP_THREADS + 32 * STRIP_FLUSH_WARPS;   // + the warps that only flush finished rows (see strip_flusher)
 constexpr int STRIP_U = 4;           // source rows per step (one barrier per step)
 constexpr int STRIP_SLOTS = 32;      // rows of the circular tile
 constexpr int STRIP_PAD = 4;         // owned column 0 sits at word 4 of a tile row; word 3 is the left garbage column
-constexpr int STRIP_FIX = 22;        // fixed-point units per intensity scale = 2^22
 constexpr unsigned STRIP_MAGIC = 0x4B400000u;   // bit pattern of 1.5 * 2^23
 constexpr unsigned FAR_REF = 0x40000000u, FAR_TWIN = 0x80000000u, FAR_INDEX = 0x3FFFFFFFu;
 
 template <int H>
 struct Strip {
-    static constexpr int OC_MAX = 240;                                   // owned columns of a strip (<= 256 - 2H)
-    static constexpr int W = OC_MAX + STRIP_PAD + 4;                     // words per tile row: pad quad + owned + garbage quad
+    static constexpr int OC_MAX = 256 - 2 * H < 240 ? 256 - 2 * H : 240;           // owned columns of a strip
+    static constexpr int W0 = OC_MAX + STRIP_PAD + 4;                             // pad quad + owned + garbage quad
+    static constexpr int W = (W0 % 32 == 0 || W0 % 32 == 16) ? W0 + 4 : W0;       // words per tile row, rows 1 and 2 apart on different banks
     static constexpr int TILE_WORDS = STRIP_SLOTS * W;
-    static_assert(H == 4 || H == 8, "halo: 4 or 8 (16-byte aligned strips, 256 source columns per block)");
-    static_assert(W % 4 == 0 && W % 32 != 0 && W / 4 <= 64, "tile rows: quads, no bank alignment, one flush pass");
-    static_assert(3 * STRIP_U + 2 * H <= STRIP_SLOTS, "deposit window + rows in flight to memory must fit the circular tile");
-    static_assert(((unsigned long long)(2 * H + 1) * (2 * H + 1) << (STRIP_FIX + 1)) < (1ull << 32), "a cell cannot overflow");
+    // fixed-point units per intensity scale: a cell collects at most (2H+1)^2 rays of less than 2 scales each
+    static constexpr int FIX = H <= 8 ? 22 : 21;
+    static_assert(H == 4 || H == 8 || H == 12, "reach of the tile path");
+    static_assert(OC_MAX % 4 == 0 && W % 4 == 0 && W / 4 <= 64, "tile rows: whole quads, one flush pass of 64 threads per row");
+    static_assert(2 * STRIP_U + 2 * H <= STRIP_SLOTS, "rows being flushed + rows being deposited must fit the circular tile");
+    static_assert(((unsigned long long)(2 * H + 1) * (2 * H + 1) << (FIX + 1)) < (1ull << 32), "a cell cannot overflow");
 };
 
 // How one image is cut into blocks (host side; the same numbers go to the kernel).
 struct StripPlan {
     int strips, oc;          // column strips and owned columns per strip (multiple of 4)
     int segs, seg_rows;      // row segments per strip and rows per segment
-    unsigned far_cap;        // list entries per block and beam (= owned pixels of a block)
+    unsigned far_cap;        // list entries per warp and beam (= the 32 columns x seg_rows pixels a warp may own)
 };
 
 inline StripPlan plan_strips(int nx, int ny, int H, int slots, int batch = 1) {
     StripPlan p;
-    const int oc_max = 240;
+    const int oc_max = 256 - 2 * H < 240 ? 256 - 2 * H : 240;
     p.strips = div_up(ny, oc_max);
     p.oc = (div_up(ny, p.strips) + 3) / 4 * 4;
     // one wave of equal blocks when that leaves segments of a useful length, else as many waves as it takes
     int segs = slots / (p.strips * batch);
     if (segs < 1) segs = 1;
     int rows = div_up(nx, segs);
-    const int min_rows = 6 * H;                      // keeps the 2H halo rows of a segment below a third of its work
+    const int min_rows = 6 * H;                      // keeps the 2H halo rows of a segment at a quarter of its work
     if (rows < min_rows) rows = min_rows < nx ? min_rows : nx;
     p.segs = div_up(nx, rows);
     p.seg_rows = div_up(nx, p.segs);
-    p.far_cap = (unsigned)p.seg_rows * (unsigned)p.oc;
+    p.far_cap = (unsigned)p.seg_rows * 32u;
     return p;
 }
 
@@ -81,12 +87,9 @@ __device__ __forceinline__ unsigned strip_mulhi_rn(unsigned a, unsigned b, unsig
     return (unsigned)(((unsigned long long)a * b + half) >> 32);
 }
 
-// 2^31 in a register pair the compiler cannot see through (it would re-materialise the constant for every ray)
-__device__ __forceinline__ unsigned long long strip_half() {
-    unsigned long long h = 0x80000000ull;
-    asm volatile("" : "+l"(h));
-    return h;
-}
+// 2^31 as a 64-bit value the assembler cannot fold (`small` = any kernel argument below 2^30, e.g. an image dimension),
+// so that it stays in one register pair for the whole kernel instead of being re-materialised for every ray
+__device__ __forceinline__ unsigned long long strip_half(int small) { return 0x80000000ull | (unsigned long long)((unsigned)small >> 30); }
 
 __device__ __forceinline__ void strip_reds4(unsigned a0, unsigned a1, unsigned w0, unsigned w1, unsigned w2, unsigned w3) {
     asm volatile(
@@ -96,6 +99,28 @@ __device__ __forceinline__ void strip_reds4(unsigned a0, unsigned a1, unsigned w
         "red.shared.add.u32 [%1+4], %5;"
         ::"r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
         : "memory");
+}
+
+// Named barriers between the depositing warps and the flushing warp (PTX producer / consumer pattern: the side that
+// does not need to wait only ARRIVES).  FULL[b]: "chunk k (k & 1 == b) is deposited"; EMPTY[b]: "its finished rows are
+// flushed and zeroed".
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
+// (barrier ids as immediates: with a register id the block would reserve all 16 hardware barriers)
+__device__ __forceinline__ void named_sync(int base, int odd) {
+    if (base == BAR_FULL) { if (odd) asm volatile("bar.sync 2, %0;" ::"n"(STRIP_BLOCK) : "memory"); else asm volatile("bar.sync 1, %0;" ::"n"(STRIP_BLOCK) : "memory"); }
+    else { if (odd) asm volatile("bar.sync 4, %0;" ::"n"(STRIP_BLOCK) : "memory"); else asm volatile("bar.sync 3, %0;" ::"n"(STRIP_BLOCK) : "memory"); }
+}
+__device__ __forceinline__ void named_arrive(int base, int odd) {
+    if (base == BAR_FULL) { if (odd) asm volatile("bar.arrive 2, %0;" ::"n"(STRIP_BLOCK) : "memory"); else asm volatile("bar.arrive 1, %0;" ::"n"(STRIP_BLOCK) : "memory"); }
+    else { if (odd) asm volatile("bar.arrive 4, %0;" ::"n"(STRIP_BLOCK) : "memory"); else asm volatile("bar.arrive 3, %0;" ::"n"(STRIP_BLOCK) : "memory"); }
+}
+
+// A streaming load whose position in the instruction stream is fixed (volatile asm keeps its order against the
+// shared-memory atomics): the prefetch of source row i + U is issued right AFTER row i has been deposited, into the
+// very registers row i occupied -- the compiler otherwise loads into fresh registers and copies them back, and the
+// copy waits for the load ("register ring").
+__device__ __forceinline__ void strip_prefetch(float& dst, const float* p) {
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst) : "l"(p));
 }
 
 // Block-uniform description of the rows a source row may deposit into.
@@ -112,6 +137,15 @@ __device__ __forceinline__ RowWin row_window(int i, int R0, int R1, int nx) {
     RowWin w;
     w.sub = STRIP_MAGIC + (unsigned)lo;
     w.span = (unsigned)max(hi - lo + 1, 0);
+    w.slot = (unsigned)i - STRIP_MAGIC;
+    return w;
+}
+
+template <int H>
+__device__ __forceinline__ RowWin row_window_interior(int i) {
+    RowWin w;
+    w.sub = STRIP_MAGIC - (unsigned)H;
+    w.span = 2u * H;
     w.slot = (unsigned)i - STRIP_MAGIC;
     return w;
 }
@@ -135,79 +169,125 @@ __device__ __forceinline__ ColWin col_window(int j, int C0, int oc_plan, int ny,
     return w;
 }
 
-// Is (i, j, D) a TILE ray as far as geometry goes (block-independent)?  kx, ky = floor(D).
+// Is (i, j, D) a TILE ray as far as geometry goes (block-independent)?  bx, by = bit patterns of D + 1.5 * 2^23 rounded down.
 template <int H>
-__device__ __forceinline__ bool tile_class(int i, int j, int kx, int ky, int nx, int ny) {
+__device__ __forceinline__ bool tile_class(int i, int j, unsigned bx, unsigned by, int nx, int ny) {
+    const int kx = (int)(bx - STRIP_MAGIC), ky = (int)(by - STRIP_MAGIC);
     return (unsigned)(kx + H) < 2u * H && (unsigned)(ky + H) < 2u * H && (unsigned)(i + kx) < (unsigned)(nx - 1) &&
            (unsigned)(j + ky) < (unsigned)(ny - 1);
 }
 
-// The deposit of one ray into the circular tile(s).  Everything up to the atomics is branch-free, so that the chains
-// of consecutive rays interleave.  Returns whether the ray went into the tile.
+// The deposit of one ray into the circular tile(s).  Returns whether the ray went into the tile; bx / by come back for
+// the caller's list test.
 //   t = D + 1.5 * 2^23 rounded down carries floor(D) in its low mantissa bits (|D| < 2^22; NaN, Inf and anything
 //   larger land far outside every window), and u = D + ((M + 1) - t) rounded towards zero is 1 + (D - floor D) in
 //   one rounding, below 2 by construction: its mantissa is the bilinear fraction in 0.23 fixed point.
 template <int W, bool TWIN>
 __device__ __forceinline__ bool strip_deposit(const RowWin& rw, const ColWin& cw, float v, float dx, float dy, float scale,
-                                              unsigned vmin_bits, unsigned vspan, unsigned twin_off, unsigned long long half) {
+                                              unsigned vmin_bits, unsigned vspan, unsigned twin_off, unsigned long long half,
+                                              unsigned& bx, unsigned& by) {
     constexpr float M = 12582912.f;
     const float tx = __fadd_rd(dx, M), ty = __fadd_rd(dy, M);
-    const unsigned bx = __float_as_uint(tx), by = __float_as_uint(ty);
+    bx = __float_as_uint(tx); by = __float_as_uint(ty);
     const bool ok = (bx - rw.sub) < rw.span && (by - cw.sub) < cw.span && (__float_as_uint(v) - vmin_bits) < vspan;
-    const unsigned fx = __float_as_uint(__fadd_rz(dx, (M + 1.f) - tx)) << 9, fy = __float_as_uint(__fadd_rz(dy, (M + 1.f) - ty)) << 9;
-    const unsigned V = __float2uint_rn(v * scale);
-    const unsigned V1 = strip_mulhi_rn(V, fx, half), V0 = V - V1;
-    const unsigned w1 = strip_mulhi_rn(V0, fy, half), w0 = V0 - w1;
-    const unsigned w3 = strip_mulhi_rn(V1, fy, half), w2 = V1 - w3;
-    const unsigned s0 = (bx + rw.slot) & (STRIP_SLOTS - 1), s1 = (bx + rw.slot + 1u) & (STRIP_SLOTS - 1);
-    const unsigned col = cw.addr + by * 4u;
-    const unsigned a0 = col + s0 * (W * 4u), a1 = col + s1 * (W * 4u);
     if (ok) {
+        const unsigned fx = __float_as_uint(__fadd_rz(dx, (M + 1.f) - tx)) << 9, fy = __float_as_uint(__fadd_rz(dy, (M + 1.f) - ty)) << 9;
+        // round(v * scale) for v * scale < 2^23 on the FMA pipe: 2^23 + x has an ulp of 1
+        const unsigned V = __float_as_uint(fmaf(v, scale, 8388608.f)) - 0x4B000000u;
+        const unsigned V1 = strip_mulhi_rn(V, fx, half), V0 = V - V1;
+        const unsigned w1 = strip_mulhi_rn(V0, fy, half), w0 = V0 - w1;
+        const unsigned w3 = strip_mulhi_rn(V1, fy, half), w2 = V1 - w3;
+        const unsigned s0 = (bx + rw.slot) & (STRIP_SLOTS - 1), s1 = (bx + rw.slot + 1u) & (STRIP_SLOTS - 1);
+        // TWIN: the ray goes to the tile at +0 and to the one at +twin_off; otherwise only to the tile at +twin_off
+        const unsigned col = cw.addr + by * 4u + (TWIN ? 0u : twin_off);
+        const unsigned a0 = col + s0 * (W * 4u), a1 = col + s1 * (W * 4u);
         strip_reds4(a0, a1, w0, w1, w2, w3);
         if (TWIN) strip_reds4(a0 + twin_off, a1 + twin_off, w0, w1, w2, w3);
     }
     return ok;
 }
 
-// A ray for the list: 16 bytes on this block's slice.
-__device__ __forceinline__ void strip_push(uint4* slice, unsigned* counter, unsigned flags, int index, float v, float dx, float dy) {
-    const unsigned k = atomicAdd(counter, 1u);
-    slice[k] = make_uint4(flags | (unsigned)index, __float_as_uint(v), __float_as_uint(dx), __float_as_uint(dy));
+// The rays a warp could not give to any tile go on the WARP's private slice of the list: no atomics, the count lives
+// in a register.  Called by all 32 lanes (`push` = this lane has an entry).
+__device__ __forceinline__ void strip_push(uint4* slice, unsigned& count, bool push, unsigned head, float v, float dx, float dy) {
+    const unsigned mask = __ballot_sync(FULL_MASK, push);
+    if (push) slice[count + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u))] =
+        make_uint4(head, __float_as_uint(v), __float_as_uint(dx), __float_as_uint(dy));
+    count += __popc(mask);
 }
 
-// Rows [ra, rb] (at most 4) of the circular tile -> image, and their slots back to zero.  Thread q of a 64-thread
-// group handles words 4q .. 4q+3 of its row: quad 0 is the pad + left garbage column, quads 1 .. oc/4 the owned
-// columns, the next one the right garbage column.  `store` rows are written, the others (garbage rows) only zeroed.
-// Returns the integer sum of what this thread stored (for the running sum of a beam).
-template <int W, bool ACC>
-__device__ __forceinline__ unsigned long long strip_flush(unsigned* tile, float* out, int ra, int rb, int R0, int R1, int C0, int oc,
-                                                          int ny, float inv_scale, bool vec) {
-    const int tid = threadIdx.x;
-    const int r = ra + (tid >> 6), q = tid & 63;
+// The flushing warp's loop over the chunks of a segment: wait until chunk k is deposited, write the rows no later source
+// row can reach (plain 128-bit stores, or `out +=` in ACC mode), zero their slots, release them.  Two rows at a time, a
+// lane handling the quads lane, lane + 32 of each and issuing all its loads first: four shared-memory (and, in ACC mode,
+// four global) loads in flight per lane, which is what lets ONE warp keep up with the eight depositing ones.
+// NT tiles (beams) side by side in shared memory, one image each.  Returns the integer sum of what this lane stored from
+// tile NT-1.
+template <int H, int W, int NT, bool ACC, bool SUM>
+__device__ __forceinline__ unsigned long long strip_flusher(unsigned* tiles, float* const* outs, int R0, int R1, int C0, int oc, int nx, int ny,
+                                                            float inv_scale, bool vec) {
+    constexpr int U = STRIP_U, Q = W / 4, NQ = (Q + 31) / 32, RB = 2;
+    const int lane = threadIdx.x & 31;
+    const int s_begin = max(R0 - H, 0), s_end = min(R1 + H, nx);
+    const int n_chunks = (s_end - s_begin + U - 1) / U;
+    int flush_next = R0 - 1;
     unsigned long long sum = 0ull;
-    if (r <= rb && q < W / 4) {
-        uint4* p = reinterpret_cast<uint4*>(tile + (r & (STRIP_SLOTS - 1)) * W) + q;
-        const uint4 u = *p;
-        *p = make_uint4(0u, 0u, 0u, 0u);
-        const int c = 4 * (q - 1);                     // first owned column of this quad, relative to C0
-        if (r >= R0 && r < R1 && q >= 1 && c < oc) {
-            float4 o = make_float4((float)u.x * inv_scale, (float)u.y * inv_scale, (float)u.z * inv_scale, (float)u.w * inv_scale);
-            float* g = out + (size_t)r * ny + C0 + c;
-            if (vec) {
-                if (ACC) {
-                    const float4 b = *reinterpret_cast<const float4*>(g);
-                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                *reinterpret_cast<float4*>(g) = o;
-                sum = (unsigned long long)u.x + u.y + u.z + u.w;
-            } else {
-                const float e[4] = {o.x, o.y, o.z, o.w};
-                const unsigned ue[4] = {u.x, u.y, u.z, u.w};
+    for (int k = 0; k < n_chunks; ++k) {
+        const int s = s_begin + k * U;
+        named_sync(BAR_FULL, k & 1);
+        const int final_row = k == n_chunks - 1 ? R1 - 1 : s + U - 1 - H;
+        for (int r0 = flush_next; r0 <= final_row; r0 += RB) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (c + k < oc) { g[k] = ACC ? g[k] + e[k] : e[k]; sum += ue[k]; }
+            for (int t = 0; t < NT; ++t) {
+                uint4 u[RB][NQ];
+                float4 b[RB][NQ];
+                bool mine[RB][NQ];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int r = r0 + rr;
+                    uint4* row = reinterpret_cast<uint4*>(tiles + t * (STRIP_SLOTS * W) + (r & (STRIP_SLOTS - 1)) * W);
+                    const float4* g = reinterpret_cast<const float4*>(outs[t] + (size_t)r * ny + C0 - 4);   // quad q starts at column C0 + 4 (q - 1)
+#pragma unroll
+                    for (int e = 0; e < NQ; ++e) {
+                        const int q = 32 * e + lane;
+                        u[rr][e] = make_uint4(0u, 0u, 0u, 0u);
+                        b[rr][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        // row R0 - 1 is the upper garbage row, quad 0 the pad + left garbage column, quads beyond oc the right
+                        // garbage column: zeroed, never stored
+                        mine[rr][e] = r <= final_row && r >= R0 && q >= 1 && 4 * (q - 1) < oc;
+                        if (r <= final_row && q < Q) { u[rr][e] = row[q]; row[q] = make_uint4(0u, 0u, 0u, 0u); }
+                        if (ACC && vec && mine[rr][e]) b[rr][e] = g[q];
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    float* g = outs[t] + (size_t)(r0 + rr) * ny + C0 - 4;
+#pragma unroll
+                    for (int e = 0; e < NQ; ++e) {
+                        if (!mine[rr][e]) continue;
+                        const int q = 32 * e + lane;
+                        const uint4 w = u[rr][e];
+                        float4 o = make_float4((float)w.x * inv_scale, (float)w.y * inv_scale, (float)w.z * inv_scale, (float)w.w * inv_scale);
+                        if (vec) {
+                            if (ACC) { o.x += b[rr][e].x; o.y += b[rr][e].y; o.z += b[rr][e].z; o.w += b[rr][e].w; }
+                            *(reinterpret_cast<float4*>(g) + q) = o;
+                            if (SUM && t == NT - 1) sum += (unsigned long long)w.x + w.y + w.z + w.w;
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+                            const unsigned wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4)
+                                if (4 * (q - 1) + e4 < oc) {
+                                    float* ge = g + 4 * q + e4;
+                                    *ge = ACC ? *ge + ov[e4] : ov[e4];
+                                    if (SUM && t == NT - 1) sum += wv[e4];
+                                }
+                        }
+                    }
+                }
             }
         }
+        if (final_row >= flush_next) flush_next = final_row + 1;
+        if (k + 2 < n_chunks) named_arrive(BAR_EMPTY, k & 1);      // nobody waits for the last two
     }
     return sum;
 }
