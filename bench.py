@@ -50,7 +50,8 @@ ALG_BYTES = {
     "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
     "detect": lambda n, det: 2 * (4.0 * n + 4.0 * det),       # sample + reference images in one launch: read, write counts
 }
-SLOTS = 3   # positions in flight (paresis_rt_run_positions deals them over this many streams)
+SLOTS = 4   # scratch sets; with PER_LAUNCH > 1 that many positions share each kernel launch (blockIdx.z), else they run on SLOTS streams
+PER_LAUNCH = 4
 
 
 def config_dict(**extra):
@@ -258,7 +259,7 @@ def run_gpu(args):
         with abi.on_stream():
             res = eng.compute_rt_positions(scene, plan, offsets, points, sequence_base=step * POSITIONS,
                                            n_slots=slots or args.slots, probe_label=probe_label, probe_events=pe,
-                                           buffers=state["buffers"])
+                                           buffers=state["buffers"], per_launch=args.per_launch if slots is None else 0)
         state["buffers"] = res["buffers"]
         return res
 
@@ -442,6 +443,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=SLOTS, help="membrane positions in flight on the GPU")
+    ap.add_argument("--per-launch", type=int, default=PER_LAUNCH, help="membrane positions per kernel launch (0: one launch per position, on --slots streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

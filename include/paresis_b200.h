@@ -35,6 +35,7 @@ extern "C" {
 #define PARESIS_FLAG_NONFINITE 1
 
 #define PARESIS_MAX_LAYERS 4
+#define PARESIS_MAX_HOP_BATCH 8   /* membrane positions that can share one launch (blockIdx.z) */
 
 typedef void* paresis_stream;
 typedef struct { float re, im; } paresis_c32;
@@ -136,7 +137,6 @@ int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform
  * the layer coefficients (layers_host[m].grad_obj / grad_ref / atten; its thickness pointers are ignored) and differ in
  * their images.  Experiment.py:463-474 for each item.  `work`: scratch of paresis_refract_hop_work_bytes() bytes for the
  * rays that cannot take the tiles (NULL: taken from the stream-ordered pool for the duration of the call). */
-#define PARESIS_MAX_HOP_BATCH 8
 typedef struct {
     const float* intensity_in;                      /* NULL: uniform `intensity_uniform` */
     const float* thickness[PARESIS_MAX_LAYERS];
@@ -144,6 +144,23 @@ typedef struct {
     float* out_ref;                                 /* NULL: single beam */
     double* sum_ref;                                /* *sum_ref += what the reference beam deposits inside the image; may be NULL */
 } paresis_hop_item;
+
+/* The round-1 tile hop (mode 0: out += through dense REDs, with the pipeline bookkeeping of paresis_refract_extras) for up
+ * to PARESIS_MAX_HOP_BATCH membrane positions in ONE launch -- at 2048^2 a single position does not fill the GPU (ramp,
+ * tail and per-tile set-up are two thirds of the kernel time); a grid of several positions pays them once. */
+typedef struct {
+    const float* intensity_in;
+    const float* thickness[PARESIS_MAX_LAYERS];
+    float* out_obj;
+    float* out_ref;
+    float* zero_fill[3];
+    double* zero_scalar;
+    double* sum_ref;
+} paresis_tile_hop_item;
+
+int paresis_refract_tile_batch(const paresis_tile_hop_item* items_host, int n_items, const paresis_layer* layers_host, int n_layers,
+                               float intensity_uniform, float intensity_scale, int clear_input, int nx, int ny, int* flag,
+                               paresis_stream stream);
 
 size_t paresis_refract_hop_work_bytes(int nx, int ny, int n_layers, int n_items, int dual, int has_intensity_map, int reach);
 int paresis_refract_hop_batch(const paresis_hop_item* items_host, int n_items, const paresis_layer* layers_host, int n_layers,
@@ -217,6 +234,11 @@ typedef struct {
     float* i_bs_group[PARESIS_MAX_GROUP - 1];   /* optional: further [nx][ny] buffers like i_bs (same all-zero contract).
                                   With k of them, up to k+1 energies of a detector bin share one object hop
                                   (paresis_refract_group); NULL entries end the list. */
+    int positions_per_launch;  /* paresis_rt_run_positions only: > 1 = membrane cut, hops and detector of up to this many
+                                  positions (<= n_slots, <= PARESIS_MAX_HOP_BATCH) share ONE launch each (blockIdx.z =
+                                  position) on the caller's stream, instead of one launch per position on per-slot
+                                  streams.  Needs a sphere field and detector bins of one energy; position 0 (extra
+                                  images) always runs on its own.  0 / 1 = off. */
 } paresis_rt_job;
 
 int paresis_rt_run(const paresis_rt_job* job_host, paresis_stream stream);
@@ -315,7 +337,7 @@ int paresis_detect_counts(const float* image, int nx, int ny, int oversampling, 
                           float* work, float* out, int noise, uint64_t seed, uint64_t sequence,
                           paresis_stream stream);
 
-/* The same for up to 4 images of one detector (sample, reference, propagation, white:
+/* The same for up to 8 images of one detector (sample, reference, propagation, white:
  * Experiment.py:503-514 calls detection() once per image) in a single launch; image k draws its
  * noise from sequences_host[k]. */
 int paresis_detect_counts_multi(const float* const* images_host, float* const* outs_host,
@@ -367,6 +389,10 @@ int paresis_raster_field(const double* spheres, int n_spheres, double pix_um, in
 int paresis_membrane_from_field(const float* field, int field_x, int field_y, const int64_t* offsets_host,
                                 int n_layers, int margin, int dim_x, int dim_y, float* thickness_out,
                                 paresis_stream stream);
+/* ... for up to PARESIS_MAX_HOP_BATCH positions in one launch: offsets_host[z] / thickness_out_host[z] as above. */
+int paresis_membrane_from_field_batch(const float* field, int field_x, int field_y, const int64_t* const* offsets_host,
+                                      float* const* thickness_out_host, int n_items, int n_layers, int margin, int dim_x,
+                                      int dim_y, paresis_stream stream);
 
 /* CreateSampleSphere -- Samples/createSampGeom.py:41-53. */
 int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, float* out,

@@ -30,7 +30,7 @@ EXPORTS = (
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
     "paresis_refract_layers_ex", "paresis_raster_field", "paresis_membrane_from_field",
     "paresis_two_sphere_phantom", "paresis_df_angle", "paresis_df_split", "paresis_df_scatter",
-    "paresis_refract_group", "paresis_refract_hop_batch", "paresis_refract_hop_work_bytes", "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
+    "paresis_refract_group", "paresis_refract_tile_batch", "paresis_membrane_from_field_batch", "paresis_refract_hop_batch", "paresis_refract_hop_work_bytes", "paresis_transfer_lane_create", "paresis_transfer_lane_destroy", "paresis_transfer_d2h", "paresis_transfer_wait",
 )
 
 
@@ -63,7 +63,8 @@ class RtJob(ctypes.Structure):
                 ("out_sample", ctypes.c_void_p), ("out_ref", ctypes.c_void_p), ("out_propag", ctypes.c_void_p),
                 ("out_white", ctypes.c_void_p), ("dx_pad", ctypes.c_void_p), ("dy_pad", ctypes.c_void_p),
                 ("flag", ctypes.c_void_p), ("probe", ctypes.c_int), ("probe_start", ctypes.c_void_p),
-                ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int), ("i_bs_group", ctypes.c_void_p * (MAX_GROUP - 1))]
+                ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int), ("i_bs_group", ctypes.c_void_p * (MAX_GROUP - 1)),
+                ("positions_per_launch", ctypes.c_int)]
 
 
 class GroupEnergy(ctypes.Structure):

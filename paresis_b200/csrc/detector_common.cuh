@@ -15,7 +15,7 @@ __device__ __forceinline__ int reflect_index(int q, int n) {
     return q;
 }
 
-constexpr int DT_MAX_IMAGES = 4;
+constexpr int DT_MAX_IMAGES = 8;
 
 struct DetImages {
     const float* img[DT_MAX_IMAGES];

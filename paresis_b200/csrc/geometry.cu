@@ -344,6 +344,59 @@ extern "C" int paresis_membrane_from_field(const float* field, int field_x, int 
     return PARESIS_OK;
 }
 
+// The same for several positions in one launch (blockIdx.z): the windows of different positions overlap in the field,
+// so a batch also re-uses what the previous position pulled into L2.
+struct MembraneBatch {
+    LayerOffsets off[PARESIS_MAX_HOP_BATCH];
+    float* out[PARESIS_MAX_HOP_BATCH];
+};
+
+__global__ void __launch_bounds__(256)
+membrane_from_field_batch_kernel(const float* __restrict__ field, int field_x, int field_y, const MembraneBatch b, int n_layers, int margin,
+                                 int dim_x, int dim_y) {
+    const int c0 = blockIdx.x * 1024 + threadIdx.x;
+    const int r = blockIdx.y;
+    const LayerOffsets& off = b.off[blockIdx.z];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < n_layers; ++l) {
+        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c0;
+        if (fr < 0 || fr >= field_x) continue;
+        const float* src = field + (size_t)fr * field_y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long f = fc + 256 * k;
+            if (c0 + 256 * k < dim_y && f >= 0 && f < field_y) acc[k] += __ldg(src + f);
+        }
+    }
+    float* o = b.out[blockIdx.z] + (size_t)r * dim_y + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (c0 + 256 * k < dim_y) o[256 * k] = acc[k];
+}
+
+extern "C" int paresis_membrane_from_field_batch(const float* field, int field_x, int field_y, const int64_t* const* offsets_host,
+                                                 float* const* thickness_out_host, int n_items, int n_layers, int margin, int dim_x,
+                                                 int dim_y, paresis_stream stream) {
+    if (!field || !offsets_host || !thickness_out_host || n_items < 1 || n_items > PARESIS_MAX_HOP_BATCH || field_x < 1 || field_y < 1 ||
+        n_layers < 1 || n_layers > MAX_MEMBRANE_LAYERS || margin < 0 || dim_x < 1 || dim_y < 1) {
+        set_last_error("paresis_membrane_from_field_batch: bad arguments (items 1..%d, layers 1..%d)", PARESIS_MAX_HOP_BATCH, MAX_MEMBRANE_LAYERS);
+        return PARESIS_ERR_ARG;
+    }
+    MembraneBatch b{};
+    for (int z = 0; z < n_items; ++z) {
+        if (!offsets_host[z] || !thickness_out_host[z]) { set_last_error("paresis_membrane_from_field_batch: item %d is incomplete", z); return PARESIS_ERR_ARG; }
+        for (int l = 0; l < n_layers; ++l) {
+            b.off[z].x[l] = offsets_host[z][2 * l];
+            b.off[z].y[l] = offsets_host[z][2 * l + 1];
+        }
+        b.out[z] = thickness_out_host[z];
+    }
+    membrane_from_field_batch_kernel<<<dim3(div_up(dim_y, 1024), dim_x, n_items), 256, 0, (cudaStream_t)stream>>>(
+        field, field_x, field_y, b, n_layers, margin, dim_x, dim_y);
+    PARESIS_LAUNCH_CHECK("membrane_from_field_batch_kernel");
+    return PARESIS_OK;
+}
+
 extern "C" int paresis_sphere_map(double radius_um, int dim_x, int dim_y, double pix_um, float* out,
                                   paresis_stream stream) {
     if (!out || dim_x < 1 || dim_y < 1 || !(pix_um > 0)) { set_last_error("paresis_sphere_map: bad arguments"); return PARESIS_ERR_ARG; }

@@ -179,6 +179,143 @@ struct SlotEvents {
 SlotEvents g_events;
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Several positions per launch.  A position at 2048^2 is 18 pixels per resident thread: ramp, tail and per-block set-up
+// of its kernels cannot be amortised inside one position ("What bounds the hops").  Here the membrane cut,
+// each hop and the detector of up to `positions_per_launch` positions are ONE launch each (blockIdx.z = position, slot
+// z's scratch), all on the caller's stream.  Position 0 (propagation + white images, Experiment.py:488-498) runs alone.
+// ---------------------------------------------------------------------------------------------------------------
+static bool single_energy_bins(const paresis_rt_job* job) {
+    for (int e = 0; e < job->n_energies; ++e)
+        if (!job->energies_host[e].close_bin) return false;
+    return true;
+}
+
+static int run_positions_batched(const paresis_rt_job* job, const paresis_membrane* mem, const paresis_rt_position* positions,
+                                 int n_positions, paresis_rt_slot* slots, int n_slots, paresis_stream stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)job->nx * job->ny, nd = (size_t)job->det_x * job->det_y;
+    int per = job->positions_per_launch;
+    if (per > n_slots) per = n_slots;
+    if (per > PARESIS_MAX_HOP_BATCH) per = PARESIS_MAX_HOP_BATCH;
+    for (int k = 0; k < n_slots; ++k)
+        if (slots[k].i_bs_dirty) { PARESIS_CUDA(cudaMemsetAsync(slots[k].i_bs, 0, sizeof(float) * n, s)); slots[k].i_bs_dirty = 0; }
+
+    auto run_group = [&](const int* idx, int g) -> int {
+        const paresis_rt_position* pos[PARESIS_MAX_HOP_BATCH];
+        const int64_t* offs[PARESIS_MAX_HOP_BATCH];
+        float* thick[PARESIS_MAX_HOP_BATCH];
+        void *ev0 = nullptr, *ev1 = nullptr;              // probe events of the first probed position of the group
+        for (int z = 0; z < g; ++z) {
+            pos[z] = &positions[idx[z]];
+            if (!pos[z]->offsets_host || !pos[z]->thickness) {
+                set_last_error("paresis_rt_run_positions: position %d lacks offsets or a thickness buffer", idx[z]);
+                return PARESIS_ERR_ARG;
+            }
+            offs[z] = pos[z]->offsets_host; thick[z] = pos[z]->thickness;
+            if (!ev0 && pos[z]->probe_start && pos[z]->probe_end) { ev0 = pos[z]->probe_start; ev1 = pos[z]->probe_end; }
+        }
+        auto probe = [&](int kind, bool start) {
+            if (job->probe == kind && ev0) cudaEventRecord((cudaEvent_t)(start ? ev0 : ev1), s);
+        };
+        probe(4, true);
+        int rc = paresis_membrane_from_field_batch(mem->field, mem->field_x, mem->field_y, offs, thick, g, mem->n_layers, mem->margin,
+                                                   job->nx, job->ny, stream);
+        probe(4, false);
+        if (rc) return rc;
+        int ibin = 0;
+        for (int e = 0; e < job->n_energies; ++e) {
+            const paresis_rt_energy& en = job->energies_host[e];
+            if (en.n_hop1 < 1 || en.n_hop2 < 1) { set_last_error("paresis_rt_run_positions: energy %d has an empty hop", e); return PARESIS_ERR_ARG; }
+            paresis_tile_hop_item h1[PARESIS_MAX_HOP_BATCH] = {}, h2[PARESIS_MAX_HOP_BATCH] = {};
+            for (int z = 0; z < g; ++z) {
+                const paresis_rt_slot& sl = slots[z];
+                for (int m = 0; m < en.n_hop1; ++m) h1[z].thickness[m] = en.hop1[m].thickness ? en.hop1[m].thickness : thick[z];
+                h1[z].out_obj = sl.i_bs;
+                h1[z].zero_fill[0] = sl.acc_sample;          // every energy closes its bin here: fresh accumulators each time
+                h1[z].zero_fill[1] = sl.acc_ref;
+                h1[z].zero_scalar = pos[z]->means ? pos[z]->means + e : nullptr;
+                for (int m = 0; m < en.n_hop2; ++m) h2[z].thickness[m] = en.hop2[m].thickness ? en.hop2[m].thickness : thick[z];
+                h2[z].intensity_in = sl.i_bs;
+                h2[z].out_obj = sl.acc_sample;
+                h2[z].out_ref = sl.acc_ref;
+                h2[z].sum_ref = pos[z]->means ? pos[z]->means + e : nullptr;
+            }
+            if (e == 0) probe(1, true);
+            rc = paresis_refract_tile_batch(h1, g, en.hop1, en.n_hop1, en.intensity_membrane, en.intensity_membrane, 0, job->nx, job->ny,
+                                            job->flag, stream);
+            if (e == 0) probe(1, false);
+            if (rc) return rc;
+            if (e == 0) probe(2, true);
+            rc = paresis_refract_tile_batch(h2, g, en.hop2, en.n_hop2, 0.f, en.intensity_membrane, 1, job->nx, job->ny, job->flag, stream);
+            if (e == 0) probe(2, false);
+            if (rc) return rc;
+            // the detector: sample + reference image of up to four positions per launch (Experiment.py:501-521)
+            for (int z0 = 0; z0 < g; z0 += 4) {
+                const int gz = g - z0 < 4 ? g - z0 : 4;
+                const float* in_k[8]; float* out_k[8]; uint64_t seq_k[8];
+                for (int z = 0; z < gz; ++z) {
+                    const uint64_t seq = pos[z0 + z]->sequence + (uint64_t)ibin * 4;
+                    in_k[2 * z] = slots[z0 + z].acc_sample; out_k[2 * z] = pos[z0 + z]->out_sample + (size_t)ibin * nd; seq_k[2 * z] = seq;
+                    in_k[2 * z + 1] = slots[z0 + z].acc_ref; out_k[2 * z + 1] = pos[z0 + z]->out_ref + (size_t)ibin * nd; seq_k[2 * z + 1] = seq + 1;
+                }
+                if (ibin == 0 && z0 == 0) probe(3, true);
+                rc = paresis_detect_counts_multi(in_k, out_k, seq_k, 2 * gz, job->nx, job->ny, job->oversampling, job->det_x, job->det_y,
+                                                 job->src_kernel, job->src_half, job->psf_kernel, job->psf_half, job->detect_work,
+                                                 job->noise, job->seed, stream);
+                if (ibin == 0 && z0 == 0) probe(3, false);
+                if (rc) return rc;
+            }
+            ++ibin;
+        }
+        return PARESIS_OK;
+    };
+
+    std::vector<paresis_rt_energy> energies(job->energies_host, job->energies_host + job->n_energies);
+    int group[PARESIS_MAX_HOP_BATCH], g = 0;
+    for (int p = 0; p < n_positions; ++p) {
+        const paresis_rt_position& pos = positions[p];
+        if (!pos.first_point) {
+            group[g++] = p;
+            if (g == per) { int rc = run_group(group, g); if (rc) return rc; g = 0; }
+            continue;
+        }
+        // position 0: on its own, through the per-position pipeline, after what is pending (it shares slot 0)
+        if (g) { int rc = run_group(group, g); if (rc) return rc; g = 0; }
+        if (!pos.offsets_host || !pos.thickness) {
+            set_last_error("paresis_rt_run_positions: position %d lacks offsets or a thickness buffer", p);
+            return PARESIS_ERR_ARG;
+        }
+        int rc = paresis_membrane_from_field(mem->field, mem->field_x, mem->field_y, pos.offsets_host, mem->n_layers, mem->margin,
+                                             job->nx, job->ny, pos.thickness, stream);
+        if (rc) return rc;
+        for (int e = 0; e < job->n_energies; ++e) {
+            const paresis_rt_energy& src = job->energies_host[e];
+            paresis_rt_energy& dst = energies[e];
+            for (int m = 0; m < PARESIS_MAX_LAYERS; ++m) {
+                dst.hop1[m].thickness = src.hop1[m].thickness ? src.hop1[m].thickness : pos.thickness;
+                dst.hop2[m].thickness = src.hop2[m].thickness ? src.hop2[m].thickness : pos.thickness;
+                dst.propag[m].thickness = src.propag[m].thickness ? src.propag[m].thickness : pos.thickness;
+            }
+        }
+        paresis_rt_job j = *job;
+        j.energies_host = energies.data();
+        j.first_point = 1;
+        j.i_bs = slots[0].i_bs; j.acc_sample = slots[0].acc_sample; j.acc_ref = slots[0].acc_ref;
+        j.acc_propag = slots[0].acc_propag; j.acc_white = slots[0].acc_white;
+        j.i_bs_dirty = 0;
+        j.means = pos.means;
+        j.out_sample = pos.out_sample; j.out_ref = pos.out_ref; j.out_propag = pos.out_propag; j.out_white = pos.out_white;
+        j.sequence = pos.sequence;
+        j.probe = 0;
+        j.dx_pad = j.dy_pad = nullptr;
+        rc = paresis_rt_run(&j, stream);
+        if (rc) return rc;
+    }
+    if (g) { int rc = run_group(group, g); if (rc) return rc; }
+    return PARESIS_OK;
+}
+
 extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis_membrane* mem,
                                         const paresis_rt_position* positions, int n_positions,
                                         paresis_rt_slot* slots, int n_slots, paresis_stream stream) {
@@ -187,6 +324,8 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
         return PARESIS_ERR_ARG;
     }
     if (n_positions == 0) return PARESIS_OK;
+    if (job->positions_per_launch > 1 && mem->field && !job->i_bs_group[0] && single_energy_bins(job))
+        return run_positions_batched(job, mem, positions, n_positions, slots, n_slots, stream);
     int rc = g_events.ensure(n_slots);
     if (rc) return rc;
     cudaStream_t main_stream = (cudaStream_t)stream;

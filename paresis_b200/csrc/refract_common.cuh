@@ -31,6 +31,21 @@ struct RefractArgs {
     float intensity_scale;   // > 0: nominal beam intensity, enables the fixed-point tile kernel (refract_tile.cuh)
 };
 
+// The tile hop for several membrane positions in one launch (blockIdx.z): what differs between the positions.
+constexpr int LEAN_MAX_BATCH = 8;
+struct LeanItem {
+    const float* map[PARESIS_MAX_LAYERS];
+    const float* I_in;
+    float* out_obj;
+    float* out_ref;
+    float* zero[3];
+    double* sum_ref;
+    double* zero_scalar;
+};
+struct LeanArgs : RefractArgs<float> {
+    LeanItem z[LEAN_MAX_BATCH];
+};
+
 // refractionFileNumba2.py:59-64: |D| < 1e-12 -> 0; |D| > N kills the ray (I = 0, D = 0).
 __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, float cy) {
     if (fabsf(dx) < 1e-12f) dx = 0.f;
@@ -45,6 +60,9 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
 int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 // The same with fewer instructions per ray (refract_lean.cu): integer bilinear split, deferred misses.
 int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
+// ... for n_batch positions at once: a.z[0 .. n_batch) hold their images, the RefractArgs part the shared coefficients
+// (its own map / image pointers are ignored, only out_ref != nullptr and I_in != nullptr select the kernel shape).
+int dispatch_refract_lean_batch(int n_layers, const LeanArgs& a, int n_batch, cudaStream_t s);
 
 // Stand-alone splat through fixed-point shared-memory tiles (splat_tile.cu): variant 3 of paresis_splat.
 int launch_splat_tile(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, cudaStream_t s);

@@ -95,7 +95,8 @@ constexpr unsigned MISS_REF = 0x40000000u, MISS_TWIN = 0x80000000u;
 
 template <int NM, bool DUAL, bool HAS_I, int TR, int MQ>
 __global__ void __launch_bounds__(TILE_COLS, LEAN_MIN_BLOCKS(DUAL, NM))
-refract_lean_kernel(const RefractArgs<float> a) {
+refract_lean_kernel(const LeanArgs a) {
+    const LeanItem& it = a.z[blockIdx.z];          // this block's membrane position
     constexpr int H = 4;
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H, NT = DUAL ? 2 : 1;
     static_assert(((1ull << 32) / (TR * TILE_COLS)) >= (2ull << FIX_BITS), "rays up to 2 x intensity_scale must fit the fixed-point tile");
@@ -134,14 +135,14 @@ refract_lean_kernel(const RefractArgs<float> a) {
     for (int k = 0; k < RING - 1; ++k) {
         const int o = min(max(off + (k - 1) * f.ny, jc), last);
 #pragma unroll
-        for (int m = 0; m < NM; ++m) row[k][m] = __ldg(a.map[m] + o);
+        for (int m = 0; m < NM; ++m) row[k][m] = __ldg(it.map[m] + o);
         // plain loads: with clear_input the same thread stores to this address after reading it
-        inten[k] = HAS_I ? a.I_in[o] : a.I_uniform;
+        inten[k] = HAS_I ? it.I_in[o] : a.I_uniform;
     }
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-        lr[0][m][0] = __ldg(a.map[m] + off + (jc > 0 ? -1 : 0));
-        lr[0][m][1] = __ldg(a.map[m] + off + (jc < f.ny - 1 ? 1 : 0));
+        lr[0][m][0] = __ldg(it.map[m] + off + (jc > 0 ? -1 : 0));
+        lr[0][m][1] = __ldg(it.map[m] + off + (jc < f.ny - 1 ? 1 : 0));
     }
 
     // rays below vmax convert to less than 2^32 / (TR * 256) - 4 units: a whole tile cannot overflow one cell
@@ -152,14 +153,14 @@ refract_lean_kernel(const RefractArgs<float> a) {
     const float neg_log2e = -1.4426950408889634f;
     // zero-fill of the buffers the next kernel scatters into: this block's rows x 256 columns, with 128-bit stores
     // when the layout allows it, else pixel by pixel in the row loop (the host fills unused slots with a used pointer)
-    const bool zero_fill = a.zero[0] != nullptr;
+    const bool zero_fill = it.zero[0] != nullptr;
     const bool zero_vec = zero_fill && (f.ny & 3) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(a.zero[0]) | reinterpret_cast<uintptr_t>(a.zero[1]) |
-                            reinterpret_cast<uintptr_t>(a.zero[2])) & 15) == 0;
+                          ((reinterpret_cast<uintptr_t>(it.zero[0]) | reinterpret_cast<uintptr_t>(it.zero[1]) |
+                            reinterpret_cast<uintptr_t>(it.zero[2])) & 15) == 0;
     if (zero_fill && !zero_vec && live) {
         for (int r = i0; r < i1; ++r) {
             const size_t o = (size_t)r * f.ny + j;
-            a.zero[0][o] = 0.f; a.zero[1][o] = 0.f; a.zero[2][o] = 0.f;
+            it.zero[0][o] = 0.f; it.zero[1][o] = 0.f; it.zero[2][o] = 0.f;
         }
     }
     if (zero_vec) {
@@ -168,7 +169,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
             for (int r = i0 + (tid >> 6); r < i1; r += TILE_COLS / 64) {
                 const size_t o = (size_t)r * f.ny + c;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(a.zero[k] + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(it.zero[k] + o) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
@@ -181,7 +182,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
     const int tcol = tid + H - ky_lo;
     bool bad = false;
     float ref_sum = 0.f;
-    if (a.zero_scalar && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *a.zero_scalar = 0.0;
+    if (it.zero_scalar && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *it.zero_scalar = 0.0;
     __syncthreads();
 
     // a ray that cannot take the tile: remember it (16 bytes), or deposit it now if the list is full
@@ -192,9 +193,9 @@ refract_lean_kernel(const RefractArgs<float> a) {
             queue[slot] = make_uint4(flags | ((unsigned)tid << 8) | (unsigned)(i - i0), __float_as_uint(v), __float_as_uint(dx),
                                      __float_as_uint(dy));
         } else if (flags & MISS_TWIN) {
-            ref_sum += deposit_direct<true>(a.out_obj, a.out_ref, i, j, v, dx, dy, f.nx, f.ny, bad);
+            ref_sum += deposit_direct<true>(it.out_obj, it.out_ref, i, j, v, dx, dy, f.nx, f.ny, bad);
         } else {
-            const float s = deposit_direct<false>((flags & MISS_REF) ? a.out_ref : a.out_obj, nullptr, i, j, v, dx, dy, f.nx, f.ny, bad);
+            const float s = deposit_direct<false>((flags & MISS_REF) ? it.out_ref : it.out_obj, nullptr, i, j, v, dx, dy, f.nx, f.ny, bad);
             if (flags & MISS_REF) ref_sum += s;
         }
     };
@@ -228,7 +229,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
         int off2 = off + 2 * f.ny;       // (i+2, j)
         const float* pn[NM];             // (i+1, j) of each map: the address the previous step fetched from
 #pragma unroll
-        for (int m = 0; m < NM; ++m) pn[m] = a.map[m] + (off + f.ny);
+        for (int m = 0; m < NM; ++m) pn[m] = it.map[m] + (off + f.ny);
         int trow = H - kx_lo;            // the source pixel in window coordinates: (trow, tcol)
         for (int ib = i0; ib < i1; ib += RING) {
 #pragma unroll
@@ -238,13 +239,13 @@ refract_lean_kernel(const RefractArgs<float> a) {
                 const int lcur = s % 2, lnew = (s + 1) % 2;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
-                    const float* p2 = a.map[m] + off2;
+                    const float* p2 = it.map[m] + off2;
                     row[knew][m] = __ldg(p2);
                     lr[lnew][m][0] = __ldg(pn[m] - 1);
                     lr[lnew][m][1] = __ldg(pn[m] + 1);
                     pn[m] = p2;
                 }
-                inten[knew] = HAS_I ? a.I_in[off2] : a.I_uniform;
+                inten[knew] = HAS_I ? it.I_in[off2] : a.I_uniform;
                 float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
@@ -260,7 +261,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
                 const float vin = inten[kmid];
                 // Sample.py:347; ex2.approx keeps ~2e-7 relative accuracy over the attenuation range
                 const float vo = vin * ex2_fast(arg * neg_log2e);
-                if (clear_in) const_cast<float*>(a.I_in)[off2 - 2 * f.ny] = 0.f;
+                if (clear_in) const_cast<float*>(it.I_in)[off2 - 2 * f.ny] = 0.f;
                 emit(ib + s, trow, vo, vin, dxo, dyo, dxr, dyr, 0u);
                 off2 += f.ny;
                 ++trow;
@@ -284,17 +285,17 @@ refract_lean_kernel(const RefractArgs<float> a) {
                     onext = o2;
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {
-                        row[knew][m] = __ldg(a.map[m] + o2);
-                        lr[lnew][m][0] = __ldg(a.map[m] + o1 + dl);
-                        lr[lnew][m][1] = __ldg(a.map[m] + o1 + dr);
+                        row[knew][m] = __ldg(it.map[m] + o2);
+                        lr[lnew][m][0] = __ldg(it.map[m] + o1 + dl);
+                        lr[lnew][m][1] = __ldg(it.map[m] + o1 + dr);
                     }
-                    inten[knew] = HAS_I ? a.I_in[o2] : a.I_uniform;
+                    inten[knew] = HAS_I ? it.I_in[o2] : a.I_uniform;
                 }
                 const bool inner = inner_cols && i > 0 && i < f.nx - 1;   // warp-uniform
                 float dxo = 0.f, dyo = 0.f, dxr = 0.f, dyr = 0.f, arg = 0.f;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
-                    const float* t = a.map[m];
+                    const float* t = it.map[m];
                     const float mid = row[kmid][m], up = row[kup][m], dn = row[kdn][m];
                     const float lf = lr[lcur][m][0], rt = lr[lcur][m][1];
                     float gy, gx;
@@ -321,7 +322,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
                 }
                 const float vin = inten[kmid];
                 const float vo = vin * ex2_fast(arg * neg_log2e);
-                if (live && clear_in) const_cast<float*>(a.I_in)[off] = 0.f;
+                if (live && clear_in) const_cast<float*>(it.I_in)[off] = 0.f;
                 emit(i, trow, vo, vin, dxo, dyo, dxr, dyr, live ? 0u : ~0u);
                 off += f.ny;
                 ++trow;
@@ -336,19 +337,19 @@ refract_lean_kernel(const RefractArgs<float> a) {
             const int i = i0 + (int)(e.x & 0xFFu), jj = blockIdx.x * TILE_COLS + (int)((e.x >> 8) & 0xFFu);
             const float v = __uint_as_float(e.y), dx = __uint_as_float(e.z), dy = __uint_as_float(e.w);
             if (DUAL && (e.x & MISS_TWIN)) {
-                ref_sum += deposit_direct<true>(a.out_obj, a.out_ref, i, jj, v, dx, dy, f.nx, f.ny, bad);
+                ref_sum += deposit_direct<true>(it.out_obj, it.out_ref, i, jj, v, dx, dy, f.nx, f.ny, bad);
             } else {
                 const bool to_ref = DUAL && (e.x & MISS_REF);
-                const float s = deposit_direct<false>(to_ref ? a.out_ref : a.out_obj, nullptr, i, jj, v, dx, dy, f.nx, f.ny, bad);
+                const float s = deposit_direct<false>(to_ref ? it.out_ref : it.out_obj, nullptr, i, jj, v, dx, dy, f.nx, f.ny, bad);
                 if (to_ref) ref_sum += s;
             }
         }
     }
     if (bad && a.flag) atomicOr(a.flag, FLAG_NONFINITE);
-    if (DUAL && a.sum_ref) {   // one double atomic per warp
+    if (DUAL && it.sum_ref) {   // one double atomic per warp
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) ref_sum += __shfl_xor_sync(FULL_MASK, ref_sum, d);
-        if (lane == 0) atomicAdd(a.sum_ref, (double)ref_sum);
+        if (lane == 0) atomicAdd(it.sum_ref, (double)ref_sum);
     }
     const bool vec_ok = (f.ny & 3) == 0;
     const float inv_scale = a.intensity_scale / (float)(1u << FIX_BITS);
@@ -356,7 +357,7 @@ refract_lean_kernel(const RefractArgs<float> a) {
     const int sr0 = max(0, -rlo), sr1 = min(used_rows, f.nx - rlo);              // tile rows that are image rows
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
-        float* out = k == 0 ? a.out_obj : a.out_ref;
+        float* out = k == 0 ? it.out_obj : it.out_ref;
         const bool vec = vec_ok && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
         if (vec && cols_inside) flush_rows_fast<SC>(tile_smem + k * SR * SC, out, rlo, clo, sr0, sr1, f.ny, inv_scale);
         else flush_tile<SR, SC>(tile_smem + k * SR * SC, out, rlo, clo, f.nx, f.ny, inv_scale, vec, used_rows);
@@ -364,23 +365,25 @@ refract_lean_kernel(const RefractArgs<float> a) {
 }
 
 template <int NM, bool DUAL, bool HAS_I, int TR>
-static int launch_refract_lean(const RefractArgs<float>& a_in, cudaStream_t s) {
+static int launch_refract_lean(const LeanArgs& a_in, int n_batch, cudaStream_t s) {
     constexpr int H = 4, MQ = 256;   // 4 resident blocks of the two-beam hop: 2 tiles + list <= 56 KB
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     constexpr size_t smem = sizeof(unsigned) * (SR * SC * (DUAL ? 2 : 1) + 4 * MQ + 4);
-    static int slots = 0;
-    if (!slots) {
+    static int slots_of[32] = {0};   // resident blocks x SMs, per device (the attribute and the occupancy are per device)
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    if (!slots_of[dev]) {
         PARESIS_CUDA(cudaFuncSetAttribute(refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, sms = 0;
         PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ>, TILE_COLS, smem));
-        PARESIS_CUDA(cudaGetDevice(&dev));
         PARESIS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        slots = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+        slots_of[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
-    RefractArgs<float> a = a_in;
+    LeanArgs a = a_in;
     const int strips = div_up(a.f.ny, TILE_COLS);
-    a.rows = pick_tile_rows(a.f.nx, strips, slots, TR);
-    dim3 grid(strips, div_up(a.f.nx, a.rows));
+    a.rows = pick_tile_rows(a.f.nx, strips * n_batch, slots_of[dev], TR);
+    dim3 grid(strips, div_up(a.f.nx, a.rows), n_batch);
     refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ><<<grid, TILE_COLS, smem, s>>>(a);
     PARESIS_LAUNCH_CHECK("refract_lean_kernel");
     return PARESIS_OK;

@@ -13,6 +13,8 @@
 // that all blocks agree on which rays are tile rays.  Rays outside [2^-13, 2) of that scale, like rays that move
 // further than H = 12 pixels or touch the image border, go through make_ray() -- the reference's loop-frame rules --
 // in the drain launch.
+#include <type_traits>
+
 #include "strip.cuh"
 
 namespace paresis {
@@ -20,7 +22,7 @@ namespace paresis {
 constexpr int SPLAT_H = 12;     // reach of the tile path; on a membrane's field 0.16 % of the rays move further (1.9 % at H = 8)
 
 template <int H, bool ACC>
-__global__ void __launch_bounds__(STRIP_BLOCK, 5)
+__global__ void __launch_bounds__(STRIP_THREADS, 5)
 splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, const float* __restrict__ Dy, float* __restrict__ out,
                    Frame f, StripPlan p, uint4* __restrict__ far, unsigned* __restrict__ far_count, bool vec) {
     using S = Strip<H>;
@@ -43,18 +45,18 @@ splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, co
 
     {
         uint4* z = reinterpret_cast<uint4*>(tile);
-        for (int k = tid; k < S::TILE_WORDS / 4; k += STRIP_BLOCK) z[k] = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = tid; k < S::TILE_WORDS / 4; k += STRIP_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     // the intensity scale: the same 256 samples in every block
     {
         const int si = (int)(((long long)(2 * (tid >> 4) + 1) * f.nx) >> 5), sj = (int)(((long long)(2 * (tid & 15) + 1) * f.ny) >> 5);
-        const float t = tid < STRIP_THREADS ? __ldg(I + (size_t)si * f.ny + sj) : 0.f;
+        const float t = __ldg(I + (size_t)si * f.ny + sj);
         const bool good = t > 0.f && t < 3.0e38f;              // NaN fails the compares
         float sum = good ? t : 0.f;
         const unsigned cnt = __popc(__ballot_sync(FULL_MASK, good));
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, d);
-        if (lane == 0 && tid < STRIP_THREADS) { misc[tid >> 5] = __float_as_uint(sum); misc[8 + (tid >> 5)] = cnt; }
+        if (lane == 0) { misc[tid >> 5] = __float_as_uint(sum); misc[8 + (tid >> 5)] = cnt; }
     }
 
     // source rows of this block and the first U of them
@@ -81,35 +83,41 @@ splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, co
     const float scale = __uint_as_float((254u + S::FIX - mexp) << 23), inv_scale = __uint_as_float((mexp - S::FIX) << 23);
     const unsigned vmin_bits = (mexp + 9u - S::FIX) << 23, vspan = fixed_ok ? ((unsigned)(S::FIX - 8) << 23) : 0u;
 
-    if (tid >= STRIP_THREADS) {                                    // the flushing warp
-        float* const outs[1] = {out};
-        strip_flusher<H, S::W, 1, ACC, false>(tile, outs, R0, R1, C0, oc, f.nx, f.ny, inv_scale, vec);
-        return;
-    }
     const ColWin cw = col_window<H>(j, C0, p.oc, f.ny, live, (unsigned)__cvta_generic_to_shared(tile));
+    const FlushLane fl = flush_lane<S::W>(C0, oc);
+    int flush_next = R0 - 1;
     // rows whose deposit window is the full [-H, H-1] and that this block owns as source rows: most of a segment
     const int in_lo = max(R0 + H - 1, H), in_hi = min(R1 - H, f.nx - 1 - H);
+    // warp-uniform: within H columns of every lane there is no image border (all four cells of a reach-H ray are image cells)
+    const bool cols_simple = __all_sync(FULL_MASK, j - H >= 0 && j + H <= f.ny - 1);
     const unsigned long long half = strip_half(f.nx);
 
-    // the ray of source pixel (i, j): into the tile, or -- if this block owns the pixel and no block's tile takes the ray -- on the list
-    auto ray = [&](int i, const RowWin& rw, bool own_row, float v, float dx, float dy) {
+    // The ray of source pixel (i, j): into the tile, or -- if this block owns the pixel and no block's tile takes the
+    // ray -- on the list.  On interior rows away from the image border "no tile takes it" is a two-compare test, so the
+    // warps at the edge of a strip (whose rays often belong to the neighbour's tile) cost what the others cost.
+    auto ray = [&](auto IC, int i, const RowWin& rw, bool own_row, float v, float dx, float dy) {
+        constexpr bool INTERIOR = decltype(IC)::value;
         unsigned bx, by;
         const bool ok = strip_deposit<S::W, false>(rw, cw, v, dx, dy, scale, vmin_bits, vspan, 0u, half, bx, by);
-        // not deposited here although this block owns the source pixel: a tile ray whose cells belong to the neighbours, or one for the list
-        const bool cand = !ok && own_row && own_col && v != 0.f;
-        if (__any_sync(FULL_MASK, cand)) {                          // warp-uniform; rare away from the strip's edges
-            const bool push = cand && !(tile_class<H>(i, j, bx, by, f.nx, f.ny) && (__float_as_uint(v) - vmin_bits) < vspan);
-            strip_push(slice, n_far, push, (unsigned)(i * f.ny + j), v, dx, dy);
+        if (INTERIOR && cols_simple) {
+            const bool tile_ray = (bx - (STRIP_MAGIC - (unsigned)H)) < 2u * H && (by - (STRIP_MAGIC - (unsigned)H)) < 2u * H &&
+                                  (__float_as_uint(v) - vmin_bits) < vspan;
+            const bool push = !tile_ray && own_col && v != 0.f;
+            if (__any_sync(FULL_MASK, push)) strip_push(slice, n_far, push, (unsigned)(i * f.ny + j), v, dx, dy);
+        } else {
+            const bool cand = !ok && own_row && own_col && v != 0.f;
+            if (__any_sync(FULL_MASK, cand)) {
+                const bool push = cand && !(tile_class<H>(i, j, bx, by, f.nx, f.ny) && (__float_as_uint(v) - vmin_bits) < vspan);
+                strip_push(slice, n_far, push, (unsigned)(i * f.ny + j), v, dx, dy);
+            }
         }
     };
 
-    int k = 0;
-    for (int s = s_begin; s < s_end; s += U, ++k) {
-        if (k >= 2) named_sync(BAR_EMPTY, k & 1);               // the slots this chunk deposits into have been flushed
+    for (int s = s_begin; s < s_end; s += U) {
         if (s >= in_lo && s + U - 1 <= in_hi) {                    // block-uniform
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                ray(s + u, row_window_interior<H>(s + u), true, vq[u], dxq[u], dyq[u]);
+                ray(std::true_type{}, s + u, row_window_interior<H>(s + u), true, vq[u], dxq[u], dyq[u]);
                 strip_prefetch(vq[u], I + pre); strip_prefetch(dxq[u], Dx + pre); strip_prefetch(dyq[u], Dy + pre);    // row s + u + U (clamped)
                 pre = min(pre + f.ny, last_off);
             }
@@ -118,12 +126,19 @@ splat_strip_kernel(const float* __restrict__ I, const float* __restrict__ Dx, co
             for (int u = 0; u < U; ++u) {
                 const int i = s + u;
                 if (i >= s_end) break;                             // block-uniform
-                ray(i, row_window<H>(i, R0, R1, f.nx), i >= R0 && i < R1, vq[u], dxq[u], dyq[u]);
+                ray(std::false_type{}, i, row_window<H>(i, R0, R1, f.nx), i >= R0 && i < R1, vq[u], dxq[u], dyq[u]);
                 strip_prefetch(vq[u], I + pre); strip_prefetch(dxq[u], Dx + pre); strip_prefetch(dyq[u], Dy + pre);
                 pre = min(pre + f.ny, last_off);
             }
         }
-        named_arrive(BAR_FULL, k & 1);
+        __syncthreads();
+        // rows that no later source row can reach are final: out they go, by all threads, and their slots are zeroed
+        const int final_row = s + U >= s_end ? R1 - 1 : s + U - 1 - H;
+        while (flush_next <= final_row) {
+            const int rb = min(flush_next + 3, final_row);
+            strip_flush_rows<S::W, ACC>(tile, out, fl, flush_next, rb, R0, R1, oc, C0, f.ny, inv_scale, vec);
+            flush_next = rb + 1;
+        }
     }
     if (lane == 0) far_count[wid] = n_far;
 }
@@ -160,7 +175,7 @@ static int launch_variant(const float* I, const float* Dx, const float* Dy, floa
     constexpr int H = SPLAT_H;
     constexpr size_t smem = sizeof(unsigned) * (Strip<H>::TILE_WORDS + 32);
     int slots = 0;
-    int rc = g_splat_slots[ACC ? 1 : 0].get(splat_strip_kernel<H, ACC>, STRIP_BLOCK, smem, &slots);
+    int rc = g_splat_slots[ACC ? 1 : 0].get(splat_strip_kernel<H, ACC>, STRIP_THREADS, smem, &slots);
     if (rc) return rc;
     const StripPlan p = plan_strips(f.nx, f.ny, H, slots);
     const size_t slices = (size_t)p.strips * p.segs * STRIP_WARPS;
@@ -172,7 +187,7 @@ static int launch_variant(const float* I, const float* Dx, const float* Dy, floa
     unsigned* far_count = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + list_bytes);
     const bool vec = (f.ny & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     dim3 grid(p.strips, p.segs);
-    splat_strip_kernel<H, ACC><<<grid, STRIP_BLOCK, smem, s>>>(I, Dx, Dy, out, f, p, far, far_count, vec);
+    splat_strip_kernel<H, ACC><<<grid, STRIP_THREADS, smem, s>>>(I, Dx, Dy, out, f, p, far, far_count, vec);
     PARESIS_LAUNCH_CHECK("splat_strip_kernel");
     splat_drain_kernel<<<(unsigned)div_up((int)slices, 4), 128, 0, s>>>(far, far_count, p.far_cap, (unsigned)slices, out, f, flag);
     PARESIS_LAUNCH_CHECK("splat_drain_kernel");

@@ -216,6 +216,50 @@ __device__ __forceinline__ void strip_push(uint4* slice, unsigned& count, bool p
     count += __popc(mask);
 }
 
+// In-line flush by the depositing threads themselves (splat_strip.cu): thread (tid / 64, tid % 64) handles quad tid % 64
+// of row ra + tid / 64 of a pass of up to 4 rows.  Quad 0 is the pad + left garbage column, quads 1 .. oc/4 the owned
+// columns, the next one the right garbage column; rows outside [R0, R1) are garbage rows: zeroed, never stored.
+struct FlushLane {
+    int rr;            // row of the pass
+    int word;          // word offset of the quad in a tile row, or -1 for a thread beyond the row
+    int col;           // first image column of the quad; < 0: not an owned quad
+};
+
+template <int W>
+__device__ __forceinline__ FlushLane flush_lane(int C0, int oc) {
+    FlushLane l;
+    const int q = threadIdx.x & 63;
+    l.rr = threadIdx.x >> 6;
+    l.word = q < W / 4 ? 4 * q : -1;
+    l.col = (q >= 1 && 4 * (q - 1) < oc && q < W / 4) ? C0 + 4 * (q - 1) : -1;
+    return l;
+}
+
+template <int W, bool ACC>
+__device__ __forceinline__ void strip_flush_rows(unsigned* tile, float* out, const FlushLane& l, int ra, int rb, int R0, int R1, int oc,
+                                                 int C0, int ny, float inv_scale, bool vec) {
+    const int r = ra + l.rr;
+    if (r > rb || l.word < 0) return;
+    uint4* p = reinterpret_cast<uint4*>(tile + (r & (STRIP_SLOTS - 1)) * W + l.word);
+    const uint4 u = *p;
+    *p = make_uint4(0u, 0u, 0u, 0u);
+    if (r < R0 || r >= R1 || l.col < 0) return;
+    float4 o = make_float4((float)u.x * inv_scale, (float)u.y * inv_scale, (float)u.z * inv_scale, (float)u.w * inv_scale);
+    float* g = out + (size_t)r * ny + l.col;
+    if (vec) {
+        if (ACC) {
+            const float4 b = *reinterpret_cast<const float4*>(g);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        *reinterpret_cast<float4*>(g) = o;
+    } else {
+        const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (l.col - C0 + k < oc) g[k] = ACC ? g[k] + e[k] : e[k];
+    }
+}
+
 // The flushing warp's loop over the chunks of a segment: wait until chunk k is deposited, write the rows no later source
 // row can reach (plain 128-bit stores, or `out +=` in ACC mode), zero their slots, release them.  Two rows at a time, a
 // lane handling the quads lane, lane + 32 of each and issuing all its loads first: four shared-memory (and, in ACC mode,

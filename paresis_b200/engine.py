@@ -322,10 +322,14 @@ class ImageFormation:
         return cache[:n_slots]
 
     def compute_rt_positions(self, scene, plan, offsets, points, sequence_base=0, n_slots=2, probe_label=None,
-                             probe_events=None, want_means=True, buffers=None):
+                             probe_events=None, want_means=True, buffers=None, per_launch=0):
         """``len(offsets)`` membrane positions in one library call (paresis_rt_run_positions): per
         position the membrane is rasterised from ``plan`` (geometry.MembranePlan) at ``offsets[p]`` and
         the whole per-energy pipeline runs, positions alternating between ``n_slots`` streams.
+
+        ``per_launch`` > 1: up to that many positions (<= n_slots, <= 8) share ONE launch of the membrane cut, of each
+        hop and of the detector (blockIdx.z = position; paresis_rt_job.positions_per_launch) instead of running on
+        ``n_slots`` streams -- for grids where one position does not fill the GPU.  Detector bins of one energy only.
 
         ``scene.membrane`` must hold one ``Layer(PER_POSITION, ...)`` for the rasterised map.
         Returns a dict of device tensors: thickness [P, N, N], sample / reference [P, nbins, dx, dy],
@@ -338,6 +342,7 @@ class ImageFormation:
         closing = {b[-1] for b in bins[:nbins]}
         energies, keep = self._rt_energies(s, list(range(n_e)), closing)
         job, keep2 = self._rt_job(s, energies, False, 0)
+        job.positions_per_launch = int(per_launch)
         firsts = [p for p in range(n_pos) if points[p] == 0]
         f32 = dict(device=self.device, dtype=torch.float32)
         if buffers is None:

@@ -51,15 +51,16 @@ def _db(obj, energies):
 
 
 CASES = [
-    # name, grid, spectrum indices kept (None = all), points of the call, points compared with the oracle
-    pytest.param("B200_2048_mono", 2048, None, [0, 1, 2], [0, 2], id="config2-2048-mono"),
-    pytest.param("B200_4096_poly64", 4096, [0, 21, 32, 63], [0, 1], [0, 1], id="config3-4096-4of64"),
-    pytest.param("B200_8192_poly128", 8192, [10, 100], [1, 2], [1], id="config5-8192-2of128"),
+    # name, grid, spectrum indices kept (None = all), points of the call, points compared with the oracle, positions per launch
+    pytest.param("B200_2048_mono", 2048, None, [0, 1, 2, 3, 4], [0, 2, 4], 4, id="config2-2048-mono-4-per-launch"),   # what bench.py times
+    pytest.param("B200_2048_mono", 2048, None, [0, 1, 2], [1], 0, id="config2-2048-mono-3-streams"),
+    pytest.param("B200_4096_poly64", 4096, [0, 21, 32, 63], [0, 1], [0, 1], 0, id="config3-4096-4of64"),
+    pytest.param("B200_8192_poly128", 8192, [10, 100], [1, 2], [1], 0, id="config5-8192-2of128"),
 ]
 
 
-@pytest.mark.parametrize("name,n,keep,points,check", CASES)
-def test_production_path_matches_oracle_at_benchmark_grid(shim, name, n, keep, points, check):
+@pytest.mark.parametrize("name,n,keep,points,check,per_launch", CASES)
+def test_production_path_matches_oracle_at_benchmark_grid(shim, name, n, keep, points, check, per_launch):
     from paresis_b200 import geometry, workspace
     d = dict(experimentName=name, filepath="unused/", overSampling=2, nbExpPoints=len(points), simulation_type="RayT",
              expID="t", poissonNoise=False, returnDisplacement=False)
@@ -79,7 +80,7 @@ def test_production_path_matches_oracle_at_benchmark_grid(shim, name, n, keep, p
     np.random.seed(1000 + n)
     offsets = [plan.draw_offsets() for _ in points]
     eng = e._get_engine()
-    res = eng.compute_rt_positions(scene, plan, offsets, points, n_slots=3)
+    res = eng.compute_rt_positions(scene, plan, offsets, points, n_slots=max(3, per_launch), per_launch=per_launch)
     torch.cuda.synchronize()
     eng.check_flag()
 

@@ -183,8 +183,9 @@ def test_positions_in_one_call_match_one_by_one(shim, name):
     np.random.seed(77)
     offsets = [plan.draw_offsets() for _ in range(3)]
     eng = e._get_engine()
-    for slots in (1, 2, 3):
-        out = eng.compute_rt_positions(scene, plan, offsets, [0, 1, 2], n_slots=slots)
+    # (streams, positions per launch): positions on 1-3 streams, and several positions per kernel launch (blockIdx.z)
+    for slots, per in ((1, 0), (2, 0), (3, 0), (3, 3), (4, 2)):
+        out = eng.compute_rt_positions(scene, plan, offsets, [0, 1, 2], n_slots=slots, per_launch=per)
         torch.cuda.synchronize()
         eng.check_flag()
         energies = np.array([en for en, _ in scene.spectrum])
