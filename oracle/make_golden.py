@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_harness as rh  # noqa: E402
 
-GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+REPO = os.path.dirname(HERE)
+GOLD = os.path.join(REPO, "tests", "golden")
 
 
 def smooth_field(rng, shape, cells=6):
@@ -343,12 +344,98 @@ def golden_phantoms(ref):
     save("phantoms", **out)
 
 
+def golden_air_plate_scintillator(ref):
+    """Air volume, detector protection plate and scintillator efficiency (Experiment.py:451-459, :478-480, :320-333 for
+    Fresnel; Detector.py:131-182): the bundled experiment with the sphere sample, taken out of vacuum, with the C_plate of
+    the reference's Samples.xml in front of the detector and a 400 um CsI scintillator -- both models, two positions."""
+    for sim in ("RayT", "Fresnel"):
+        e = _experiment(ref, sim, "PMMA_sphere", None, None, 1.2, 50.0, (96, 128))
+        e.exp_dict["inVacuum"] = False
+        plate = ref["Sample"].AnalyticalSample()
+        plate.myName = "C_plate"
+        plate.defineCorrectValuesSample()
+        plate.getDeltaBeta(e.mySource.mySpectrum)
+        plate.getMyGeometry(e.exp_dict["studyDimensions"], e.exp_dict["studyPixelSize"], e.exp_dict["overSampling"])
+        e.myPlate = plate
+        e.myDetector.det_param["myScintillatorMaterial"] = "CsI"
+        e.myDetector.det_param["myScintillatorThickness"] = 400.0
+        e.myDetector.getBeta(e.mySource.mySpectrum)
+        e.myDetector.getSpectralEfficiency()
+        out = dict(air_db=_db(e.myAirVolume), plate_db=_db(e.myPlate), air_thickness_um=np.array(e.myAirVolume.myThickness),
+                   scintillator_beta=np.array(e.myDetector.beta, dtype=float), efficiency=np.array(e.myDetector.mySpectralEfficiency, dtype=float))
+        for point in (0, 1):
+            np.random.seed(300 + point)
+            e.myMembrane.myGeometry = []
+            e.myMembrane.getMyGeometry(e.exp_dict["studyDimensions"], e.myMembrane.membranePixelSize, 2, point, 2)
+            with rh.identity_poisson():
+                res = e.computeSampleAndReferenceImages_RT(point) if sim == "RayT" else e.computeSampleAndReferenceImages_Fresnel(point)
+            for tag, arr in zip(("sample", "reference", "propag", "white"), res[:4]):
+                if point == 0 or tag in ("sample", "reference"):
+                    out["%s_p%d" % (tag, point)] = np.asarray(arr, dtype=np.float64)
+        out["mean_energy"] = np.array(e.exp_dict["meanEnergy"])
+        save("e2e_air_plate_csi_" + sim.lower(), **out)
+
+
+def golden_spectrum_xls(ref):
+    """Source.setMySpectrum on the reference's own Sources/W_50kVp.xls (Source.py:131-240), source 'simap2' of its
+    Sources.xml, at several energy samplings.  The sheet itself (28 KB of measured data, not code) is copied next to
+    the shim's parameter files so that the drop-in reads the same bytes."""
+    import shutil
+    Source = ref["Source"].Source
+    out = {}
+    for sampling in (4.0, 2.0, 1.0):
+        s = Source()
+        s.myName = "simap2"
+        s.defineCorrectValuesSource()
+        s.source_dict["myEnergySampling"] = sampling
+        s.setMySpectrum()
+        out["spectrum_%g" % sampling] = np.array(s.mySpectrum, dtype=float)
+    save("spectrum_xls", **out)
+    dst = os.path.join(REPO, "paresis_b200", "CodePython", "Sources", "W_50kVp.xls")
+    shutil.copyfile(os.path.join(rh.REFERENCE_ROOT, "Sources", "W_50kVp.xls"), dst)
+    os.chmod(dst, 0o644)
+
+
+def golden_main_script(ref):
+    """The reference's main.py, unmodified, through runpy in the reference tree (Poisson patched to identity): the output
+    tree it writes, the images it saves and the report of saveAllParameters (Experiment.py:530-607).  The script text is
+    stored verbatim as a fixture (tests/golden/reference_main_py.txt) so that the GPU test can run THE SAME script against
+    the drop-in modules -- that is the "main.py is a drop-in" claim, tested."""
+    import runpy
+    import shutil
+    src = os.path.join(rh.REFERENCE_ROOT, "main.py")
+    results = os.path.abspath(os.path.join(ref["scratch"], "..", "Results", "Fil_Nylon_ID17"))
+    before = set(os.listdir(results))
+    rh.SAVED_IMAGES.clear()
+    np.random.seed(77)
+    with rh.identity_poisson():
+        runpy.run_path(src, run_name="__main__")
+    new = sorted(set(os.listdir(results)) - before)
+    report = [f for f in new if f.endswith(".txt")][0]
+    exp_id = report[len("Fil_Nylon_ID17_"):-4]
+    tree = []
+    for root, dirs, files in os.walk(os.path.join(results, "RayTracing_" + exp_id)):
+        for d in dirs:
+            tree.append(os.path.relpath(os.path.join(root, d), results).replace(exp_id, "<ID>") + "/")
+    out = dict(tree=np.array(sorted(tree)), report=np.array(open(os.path.join(results, report)).read().replace(exp_id, "<ID>")))
+    names = []
+    for fn, arr in rh.SAVED_IMAGES.items():
+        key = os.path.relpath(fn, "../Results/Fil_Nylon_ID17").replace(exp_id, "<ID>")
+        names.append(key)
+        out["img_%d" % (len(names) - 1)] = np.asarray(arr, dtype=np.float32)
+    out["image_names"] = np.array(names)
+    save("main_script", **out)
+    shutil.copyfile(src, os.path.join(GOLD, "reference_main_py.txt"))
+    os.chmod(os.path.join(GOLD, "reference_main_py.txt"), 0o644)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
     only = sys.argv[1:]
     for fn in (golden_splat_kernel, golden_fast_refraction, golden_detector, golden_waves, golden_geometry,
-               golden_end_to_end, golden_darkfield, golden_phantoms):
+               golden_end_to_end, golden_darkfield, golden_phantoms, golden_air_plate_scintillator, golden_spectrum_xls,
+               golden_main_script):
         if not only or fn.__name__ in only:
             print(fn.__name__)
             fn(ref)

@@ -129,7 +129,7 @@ def _install_stubs():
                         table_cache[name.strip()] = np.array(rows, dtype=float)
         return table_cache[material]
 
-    formula_to_material = {"H0.080538C0.599848O0.319614": "PMMA"}
+    formula_to_material = {"H0.080538C0.599848O0.319614": "PMMA", "C0.977O0.023": "CarbonFiber", "Cs1I1": "CsI", "C": "Carbon"}
 
     def Refractive_Index(formula, energy_kev, density):
         t = _table(formula_to_material[formula])

@@ -4,6 +4,8 @@ Same class, attribute and function names (Detector.py:19-220).  ``detection`` ru
 blur / bin / blur / Poisson chain in CUDA kernels (csrc/detector.cu); the scintillator
 efficiency scalars are host arithmetic.
 """
+import os
+
 import numpy as np
 
 import _paresis_path  # noqa: F401
@@ -34,6 +36,9 @@ class Detector:
         self.beta = []
         # extensions (ignored by the reference): deterministic / noise-free detection
         self.poissonNoise = bool(exp_dict.get("poissonNoise", True)) if isinstance(exp_dict, dict) else True
+        # test hook for drivers that build their own exp_dict (PARESIS's unmodified main.py): noise-free images
+        if os.environ.get("PARESIS_B200_POISSON", "") == "0":
+            self.poissonNoise = False
         self.seed = exp_dict.get("seed") if isinstance(exp_dict, dict) else None
         self._draws = 0
 

@@ -96,3 +96,65 @@ def read_edf(path):
 def open_image(path):
     path = str(path)
     return read_edf(path) if path.lower().endswith(".edf") else read_tiff(path)
+
+
+# ---------------------------------------------------------------------------- asynchronous writer
+class AsyncWriter:
+    """One background thread that encodes and writes images, so that disk I/O overlaps the GPU work of the next
+    membrane position (PARESIS writes ~6 images per position synchronously: main.py:98-110).  ``submit`` takes ownership
+    of a private float32 / uint16 copy made on the caller's thread; at most ``depth`` images wait in memory.  Errors
+    surface on the next ``submit`` / ``flush`` (and at interpreter exit)."""
+
+    def __init__(self, depth=16):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=depth)
+        self._error = None
+        self._thread = threading.Thread(target=self._run, name="paresis-image-writer", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            try:
+                if item is None:
+                    return
+                fn, path, image = item
+                if self._error is None:
+                    fn(path, image)
+            except BaseException as exc:          # kept for the submitting thread
+                self._error = exc
+            finally:
+                self._q.task_done()
+
+    def _raise(self):
+        if self._error is not None:
+            exc, self._error = self._error, None
+            raise exc
+
+    def submit(self, fn, path, image):
+        self._raise()
+        self._q.put((fn, path, image))
+
+    def flush(self):
+        """Block until everything submitted so far is on disk."""
+        self._q.join()
+        self._raise()
+
+
+_writer = None
+
+
+def writer():
+    """The process-wide writer thread (created on first use, flushed at interpreter exit)."""
+    global _writer
+    if _writer is None:
+        import atexit
+        _writer = AsyncWriter()
+        atexit.register(_writer.flush)
+    return _writer
+
+
+def flush_writes():
+    if _writer is not None:
+        _writer.flush()

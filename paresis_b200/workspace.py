@@ -30,7 +30,7 @@ def synthetic_sphere_rows(seed=0, count=60000):
 def make_workspace(path, sphere_rows=None, sphere_seed=0, sphere_count=60000, sphere_file=None):
     path = os.path.abspath(path)
     os.makedirs(os.path.join(path, "Samples", "Membranes"), exist_ok=True)
-    for rel in ("xmlFiles", os.path.join("Samples", "DeltaBeta")):
+    for rel in ("xmlFiles", os.path.join("Samples", "DeltaBeta"), "Sources"):
         dst = os.path.join(path, rel)
         if not os.path.lexists(dst):
             os.symlink(os.path.join(SHIM_DIR, rel), dst)

@@ -147,6 +147,7 @@ def test_main_script_writes_the_output_tree(shim, tmp_path):
     args = argparse.Namespace(experiment="Small_sphere_mono", results=str(tmp_path / "Results"), oversampling=2, points=2,
                               model="RayT", format=".tif", seed=3)
     root = main.run(args)
+    importlib.import_module("InputOutput.pagailleIO").wait_for_writes()
     files = sorted(os.path.relpath(os.path.join(dp, f), root) for dp, _, fs in os.walk(root) for f in fs)
     assert sum(f.startswith("sample/") for f in files) == 2 and sum(f.startswith("ref/") for f in files) == 2
     assert sum(f.startswith("propag/") for f in files) == 1 and sum(f.startswith("membraneThickness/") for f in files) == 2
@@ -257,3 +258,80 @@ def test_float32_results_option(shim):
     for a, b in zip(outs["float64"], outs["float32"]):
         # (two runs: the fp32 accumulation order of the few rays that bypass the tiles is not reproducible)
         assert a.dtype == np.float64 and b.dtype == np.float32 and rel_l2(b, a) < 1e-6
+
+
+def test_reference_main_script_runs_unmodified(golden, tmp_path, monkeypatch):
+    """PARESIS's OWN main.py (tests/golden/reference_main_py.txt: a verbatim copy made by oracle/make_golden.py), run with
+    runpy from a CodePython-shaped directory whose modules are the drop-in's: same output tree, same image files, same
+    images (noise off on both sides) and the same saveAllParameters report (Experiment.py:530-607) as the reference
+    produced from the same script and seed.  main.py:58-113."""
+    import re
+    import runpy
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from paresis_b200 import workspace
+    from paresis_b200.hostio import imageio
+    g = golden("main_script")
+    ws = workspace.make_workspace(str(tmp_path / "CodePython"))
+    results = tmp_path / "Results" / "Fil_Nylon_ID17"          # main.py writes to ../Results/Fil_Nylon_ID17/
+    results.mkdir(parents=True)
+    monkeypatch.setenv("PARESIS_B200_POISSON", "0")
+    monkeypatch.chdir(ws)
+    monkeypatch.syspath_prepend(workspace.SHIM_DIR)
+    for name in ("Experiment", "Sample", "Detector", "Source"):      # fresh module state, as a new interpreter would have
+        sys.modules.pop(name, None)
+    script = os.path.join(os.path.dirname(__file__), "golden", "reference_main_py.txt")
+    np.random.seed(77)
+    runpy.run_path(script, run_name="__main__")
+    importlib.import_module("InputOutput.pagailleIO").wait_for_writes()      # save_image is asynchronous
+    report = [f for f in os.listdir(results) if f.endswith(".txt")]
+    assert len(report) == 1
+    exp_id = report[0][len("Fil_Nylon_ID17_"):-4]
+    root = results / ("RayTracing_" + exp_id)
+    tree = sorted(os.path.relpath(os.path.join(dp, d), results).replace(exp_id, "<ID>") + "/" for dp, ds, _ in os.walk(root) for d in ds)
+    assert tree == list(g["tree"])
+    files = sorted(os.path.relpath(os.path.join(dp, f), results).replace(exp_id, "<ID>") for dp, _, fs in os.walk(root) for f in fs)
+    assert files == sorted(g["image_names"])
+    for k, name in enumerate(g["image_names"]):
+        img = imageio.read_tiff(str(results / name.replace("<ID>", exp_id)))
+        want = g["img_%d" % k]
+        assert img.dtype == np.float32 and img.shape == want.shape, name
+        if want.any():
+            assert rel_l2(img, want) < TOL, name
+        else:
+            assert not img.any(), name
+    # the report: everything but the wall-clock line
+    got = open(results / report[0]).read().replace(exp_id, "<ID>")
+    strip = lambda t: re.sub(r"Entire computing time: [0-9.e+-]+s", "Entire computing time: Xs", t)
+    got_lines, want_lines = strip(got).splitlines(), strip(str(g["report"])).splitlines()
+    assert got_lines == want_lines
+
+
+@pytest.mark.parametrize("model", ["RayT", "Fresnel"])
+def test_air_plate_and_scintillator_factors(shim, golden, model):
+    """Air volume (Experiment.py:452-453), scintillator efficiency (:456-459; Fresnel :326-333) and detector protection
+    plate (:478-480), end to end against the unmodified reference: experiment Small_sphere_air_plate_CsI."""
+    g = golden("e2e_air_plate_csi_" + model.lower())
+    d = dict(experimentName="Small_sphere_air_plate_CsI", filepath="unused/", overSampling=2, nbExpPoints=2, simulation_type=model,
+             expID="t", poissonNoise=False)
+    e = shim.Experiment(d)
+    assert not e.exp_dict["inVacuum"] and e.myPlate is not None
+    assert np.allclose(e.myAirVolume.myThickness, float(g["air_thickness_um"]))
+    assert np.allclose([v for _, v in e.myAirVolume.delta[0]], g["air_db"][:, 1], rtol=1e-12)
+    assert np.allclose([v for _, v in e.myAirVolume.beta[0]], g["air_db"][:, 2], rtol=1e-12)
+    assert np.allclose([v for _, v in e.myPlate.beta[0]], g["plate_db"][:, 2], rtol=1e-12)
+    assert np.allclose(np.array(e.myDetector.beta, dtype=float), g["scintillator_beta"], rtol=1e-12)
+    assert np.allclose(np.array(e.myDetector.mySpectralEfficiency, dtype=float), g["efficiency"], rtol=1e-12)
+    for point in (0, 1):
+        np.random.seed(300 + point)
+        e.myMembrane.myGeometry = []
+        e.myMembrane.getMyGeometry(e.exp_dict['studyDimensions'], e.myMembrane.membranePixelSize, 2, point, 2)
+        res = e.computeSampleAndReferenceImages_RT(point) if model == "RayT" else e.computeSampleAndReferenceImages_Fresnel(point)
+        assert rel_l2(res[0], g["sample_p%d" % point]) < TOL
+        assert rel_l2(res[1], g["reference_p%d" % point]) < TOL
+        if point == 0:
+            assert rel_l2(res[2], g["propag_p0"]) < TOL
+            assert rel_l2(res[3], g["white_p0"]) < TOL
+            # the factors really bite: the white field is far below the shot count
+            assert res[3].mean() < 0.8 * e.exp_dict["meanShotCount"]
+    assert abs(e.exp_dict["meanEnergy"] / float(g["mean_energy"]) - 1) < 1e-5

@@ -129,3 +129,71 @@ def test_source_spectra(tmp_path, monkeypatch):
     s = Source(); s.myName = "tube_W_50kVp"; s.defineCorrectValuesSource()
     with pytest.raises(ImportError, match="spekpy"):
         s.setMySpectrum()
+
+
+def test_xls_spectrum_matches_reference(tmp_path, golden):
+    """Source.setMySpectrum on PARESIS's Sources/W_50kVp.xls (Source.py:131-240: read the Energy / Flux columns with the
+    in-repo BIFF8 reader, re-bin to myEnergySampling, keep bins above 1e-3 of the flux) against the unmodified reference."""
+    import importlib
+    import os
+    import sys
+    from paresis_b200 import workspace
+    g = golden("spectrum_xls")
+    ws = workspace.make_workspace(str(tmp_path / "ws"), sphere_count=10)
+    old = os.getcwd()
+    os.chdir(ws)
+    sys.path.insert(0, workspace.SHIM_DIR)
+    try:
+        Source = importlib.import_module("Source").Source
+        for sampling in (4.0, 2.0, 1.0):
+            s = Source()
+            s.myName = "xls_W_50kVp"
+            s.defineCorrectValuesSource()
+            assert s.spectrumFromXls and s.source_dict["myEnergySampling"] == 4.0
+            s.source_dict["myEnergySampling"] = sampling
+            s.setMySpectrum()
+            want = g["spectrum_%g" % sampling]
+            got = np.array(s.mySpectrum, dtype=float)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-12, atol=0)
+            assert abs(got[:, 1].sum() - 1) < 0.05          # weights are fractions of the flux (tail bin excluded, as upstream)
+    finally:
+        os.chdir(old)
+
+
+def test_async_writer_and_geometry_from_images(tmp_path):
+    """save_image hands files to a writer thread (main.py:98-110 overlaps the next position); loadSampleGeometryFromImages
+    (createSampGeom.py:263-293) reads one thickness image per material, sorted by path, .tif / .tiff / .edf."""
+    import importlib
+    import os
+    import sys
+    from paresis_b200 import workspace
+    sys.path.insert(0, workspace.SHIM_DIR)
+    io = importlib.import_module("InputOutput.pagailleIO")
+    geom = importlib.import_module("Samples.createSampGeom")
+    rng = np.random.default_rng(3)
+    maps = {"b_second.tiff": rng.random((40, 56)) * 1e-3, "a_first.tif": rng.random((40, 56)) * 2e-3, "c_third.edf": rng.random((40, 56))}
+    folder = tmp_path / "geom" / "nested"
+    for name, arr in maps.items():
+        io.save_image(arr, str(folder / name))                 # creates the folders, returns before the file is complete
+    big = rng.random((1500, 1500))
+    for k in range(6):
+        io.save_image(big, str(tmp_path / ("big_%d.tif" % k)))
+    got, params = geom.loadSampleGeometryFromImages(str(folder), 40, 56, 1.0)      # openImage waits for the writer
+    assert params == {"myGeometryFolder": (str(folder), "")}
+    assert len(got) == 3
+    for arr, name in zip(got, ("a_first.tif", "b_second.tiff", "c_third.edf")):
+        assert arr.dtype == np.float32 and np.array_equal(arr, maps[name].astype(np.float32))
+    io.wait_for_writes()
+    assert all(os.path.getsize(tmp_path / ("big_%d.tif" % k)) > 1500 * 1500 * 4 for k in range(6))
+    with pytest.raises(Exception, match="does not exist or is incorrectly named"):
+        geom.loadSampleGeometryFromImages(str(tmp_path / "nothing_here"), 40, 56, 1.0)
+    # a failing write surfaces at the next hand-over
+    (tmp_path / "is_a_directory.tif").mkdir()
+    io.save_image(big, str(tmp_path / "is_a_directory.tif"))
+    with pytest.raises(OSError):
+        io.wait_for_writes()
+    io.wait_for_writes()                                      # the error was delivered once; the writer keeps working
+    io.save_image(big, str(tmp_path / "after.tif"))
+    io.wait_for_writes()
+    assert os.path.getsize(tmp_path / "after.tif") > 1500 * 1500 * 4
