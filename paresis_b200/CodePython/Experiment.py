@@ -363,7 +363,9 @@ class Experiment:
             f.write("\n    materials: %s" % mem.myMaterials)
             f.write("\n    Membrane geometry function: %s" % mem.myGeometryFunction)
             if mem.geom_parameters is not None:
-                for key, value in mem.geom_parameters.items():
+                # upstream lists the SAMPLE's geometry parameters under the membrane heading (Experiment.py:594-596
+                # iterates mySampleofInterest.geom_parameters); kept, so that the report is the reference's line for line
+                for key, value in (smp.geom_parameters or {}).items():
                     f.write(f'\n    {key}: {value[0]} {value[1]}')
             if mem.myGeometryFunction == "getMembraneFromFile":
                 f.write("\nMembrane geometry file: %s" % mem.myMembraneFile)
