@@ -58,7 +58,8 @@ def build_library(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    # --cudart shared: the runtime is the image's libcudart.so, not a private static copy inside the library
+    cmd = [NVCC, "-shared", "--cudart", "shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return LIB
 

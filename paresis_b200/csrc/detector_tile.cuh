@@ -281,10 +281,13 @@ template <int OS, int HS, int HP>
 static int launch_detect_tile(const DetImages& im, int n_images, int nx, int ny, int det_x, int det_y, const float* gs,
                               const float* gp, int noise, uint64_t seed, cudaStream_t st) {
     using T = DetTile<OS, HS, HP>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[32] = {false};      // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    if (!configured[dev]) {
         PARESIS_CUDA(cudaFuncSetAttribute(detect_tile_kernel<OS, HS, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-        configured = true;
+        configured[dev] = true;
     }
     const dim3 grid(div_up(det_y, DT_TY), div_up(det_x, DT_TX), n_images);
     detect_tile_kernel<OS, HS, HP><<<grid, DT_THREADS, T::SMEM, st>>>(im, nx, ny, det_x, det_y, gs, gp, noise, seed);

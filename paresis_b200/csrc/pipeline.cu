@@ -176,7 +176,7 @@ struct SlotEvents {
         return PARESIS_OK;
     }
 };
-SlotEvents g_events;
+SlotEvents g_events_of[32];     // CUDA events belong to a device
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -326,6 +326,9 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
     if (n_positions == 0) return PARESIS_OK;
     if (job->positions_per_launch > 1 && mem->field && !job->i_bs_group[0] && single_energy_bins(job))
         return run_positions_batched(job, mem, positions, n_positions, slots, n_slots, stream);
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    SlotEvents& g_events = g_events_of[(dev < 0 || dev >= 32) ? 0 : dev];
     int rc = g_events.ensure(n_slots);
     if (rc) return rc;
     cudaStream_t main_stream = (cudaStream_t)stream;

@@ -1,4 +1,4 @@
-// Argument block and ray clean-up shared by the fused refraction kernels (refraction.cu, refract_tile.cu).
+// Argument block and ray clean-up shared by the fused refraction kernels (refraction.cu, refract_lean.cu).
 #pragma once
 #include "splat.cuh"
 
@@ -56,9 +56,8 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
     if (by) dy = 0.f;
 }
 
-// Fixed-point shared-memory tile kernel (refract_tile.cu): tiles of up to 16 source rows x 256 columns, halo 4.
-int dispatch_refract_tile(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
-// The same with fewer instructions per ray (refract_lean.cu): integer bilinear split, deferred misses.
+// Fixed-point shared-memory tile kernel (refract_lean.cu): tiles of up to 16 source rows x 256 columns, halo 4, integer
+// bilinear split, deferred misses.
 int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 // ... for n_batch positions at once: a.z[0 .. n_batch) hold their images, the RefractArgs part the shared coefficients
 // (its own map / image pointers are ignored, only out_ref != nullptr and I_in != nullptr select the kernel shape).

@@ -1,4 +1,4 @@
-// Lean form of the fixed-point tile hop (refract_tile.cuh; same contract, same tile layout) -- the production hop.
+// The fixed-point tile hop (source-owner tiles + dense RED flush; helpers in tile_common.cuh) -- the production hop.
 // It spends 20-30 % fewer instructions per ray than the first tile kernel (what that bought, and what bounds the hops
 // instead, is in DESIGN.md section 3 and profiles/r01_summary.md):
 //
@@ -20,7 +20,7 @@
 // The bilinear fractions are truncated to 23 bits and the weights rounded to one fixed-point unit; end-to-end images
 // sit at the same distance from the reference as with the first tile kernel (profiles/r01_parity_distances.txt).
 #pragma once
-#include "refract_tile.cuh"
+#include "tile_common.cuh"
 
 namespace paresis {
 
@@ -125,7 +125,7 @@ refract_lean_kernel(const LeanArgs a) {
         if (tid == 0) *qcount = 0u;
     }
 
-    // Row ring as in refract_tile_kernel: slot k of step s holds row i-1+k, row i+2 is fetched now.  The row
+    // Row ring: slot k of step s holds row i-1+k, row i+2 is fetched now.  The row
     // neighbours (lr) of row i+1 are fetched now as well, from the lines the previous step brought into L1.
     constexpr int RING = 4;
     float row[RING][NM], inten[RING], lr[2][NM][2];

@@ -15,7 +15,7 @@
 #pragma once
 #include <type_traits>
 
-#include "refract_tile.cuh"   // deposit_direct, ex2_fast
+#include "tile_common.cuh"   // deposit_direct, ex2_fast
 #include "strip.cuh"
 
 namespace paresis {

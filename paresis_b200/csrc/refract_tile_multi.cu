@@ -5,13 +5,13 @@
 // delta(E), beta(E), the incident intensity.  This kernel therefore forms the thickness gradients of a row once
 // and loops over the energies of a group: each energy reads its own object-plane intensity I_bs[g], scales the
 // gradients, and deposits its sample and reference rays into the SAME pair of shared-memory tiles
-// (refract_tile.cuh), which are zeroed and flushed once per group instead of once per energy.
+// (tile_common.cuh), which are zeroed and flushed once per group instead of once per energy.
 //
 // Fixed point: the unit is sum_g(intensity_g) / 2^19 and a ray of energy g takes the tile only below
 // 2 x intensity_g, so a pixel contributes < 2^20 units over the whole group and a cell cannot overflow.
 #include <string.h>
 
-#include "refract_tile.cuh"
+#include "tile_common.cuh"
 
 namespace paresis {
 
@@ -174,15 +174,18 @@ static int launch_multi(MultiArgs a, cudaStream_t s) {
     constexpr int TR = 16, H = 4;
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     constexpr size_t smem = sizeof(unsigned) * SR * SC * 2;
-    static int slots = 0;
-    if (!slots) {
+    static int slots_of[32] = {0};             // resident blocks x SMs, per device
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    if (!slots_of[dev]) {
         PARESIS_CUDA(cudaFuncSetAttribute(refract_tile_multi_kernel<NM, TR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, sms = 0;
         PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refract_tile_multi_kernel<NM, TR, H>, TILE_COLS, smem));
-        PARESIS_CUDA(cudaGetDevice(&dev));
         PARESIS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        slots = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+        slots_of[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
+    const int slots = slots_of[dev];
     const int strips = div_up(a.f.ny, TILE_COLS);
     a.rows = pick_tile_rows(a.f.nx, strips, slots, TR);
     dim3 grid(strips, div_up(a.f.nx, a.rows));

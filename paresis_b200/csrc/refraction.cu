@@ -203,10 +203,9 @@ refract_kernel(const RefractArgs<T> a) {
 // Tuning knobs (paresis_set_tuning): deposit mode of the fused kernels, rows per warp.
 static int g_fused_mode = 2;
 static int g_rows_override = 0;
-// which fused hop kernel runs: 0 = lean fixed-point shared-memory tiles (refract_lean.cu; production, needs
-// paresis_refract_extras.intensity_scale), 1 = the first tile kernel (refract_tile.cu), -1 = one column per thread
-// straight to L2 (this file; what runs for everything else: displacement output, phase input, callers that give no
-// intensity scale)
+// which fused hop kernel runs: 0 = fixed-point shared-memory tiles (refract_lean.cu; production, needs
+// paresis_refract_extras.intensity_scale), -1 = one column per thread straight to L2 (this file; what runs for everything
+// else: displacement output, phase input, callers that give no intensity scale)
 static int g_tile_config = 0;
 
 // rows per warp: enough blocks for ~2 waves of 148 SMs x 8 resident blocks, few halo re-reads
@@ -243,7 +242,6 @@ static int dispatch_layers(const RefractArgs<float>& a, cudaStream_t s) {
     const bool dual = a.out_ref != nullptr, has_i = a.I_in != nullptr;
     const bool wd = a.dx_pad != nullptr;
     if (!wd && g_tile_config == 0 && a.intensity_scale > 0.f) return dispatch_refract_lean(NM, a, s);
-    if (!wd && g_tile_config == 1 && a.intensity_scale > 0.f) return dispatch_refract_tile(NM, a, s);
     if (dual) return has_i ? launch_refract<float, NM, true, true, true>(a, false, s)
                            : launch_refract<float, NM, true, false, true>(a, false, s);
     return has_i ? launch_refract<float, NM, false, true, true>(a, wd, s)
@@ -258,7 +256,7 @@ extern "C" int paresis_set_tuning(int key, int value) {
     switch (key) {
         case 0: g_fused_mode = value == 0 ? 0 : 2; return PARESIS_OK;
         case 1: g_rows_override = value; return PARESIS_OK;
-        case 2: g_tile_config = value < 0 ? -1 : (value == 1 ? 1 : 0); return PARESIS_OK;
+        case 2: g_tile_config = value < 0 ? -1 : 0; return PARESIS_OK;
         default: set_last_error("paresis_set_tuning: unknown key %d", key); return PARESIS_ERR_ARG;
     }
 }

@@ -130,15 +130,18 @@ int launch_splat_tile(const float* I, const float* Dx, const float* Dy, float* o
     constexpr int TR = 16, MQ = 512, H = 4;
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     constexpr size_t smem = sizeof(unsigned) * (SR * SC + 4 * MQ + 4 + TILE_COLS / 32);
-    static int slots = 0;
-    if (!slots) {
+    static int slots_of[32] = {0};             // resident blocks x SMs, per device
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    if (!slots_of[dev]) {
         PARESIS_CUDA(cudaFuncSetAttribute(splat_tile_kernel<TR, MQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, sms = 0;
         PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_tile_kernel<TR, MQ>, TILE_COLS, smem));
-        PARESIS_CUDA(cudaGetDevice(&dev));
         PARESIS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        slots = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+        slots_of[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
+    const int slots = slots_of[dev];
     const int strips = div_up(f.ny, TILE_COLS);
     const int rows = f.nx >= 64 ? pick_tile_rows(f.nx, strips, slots, TR) : min(f.nx, TR);
     dim3 grid(strips, div_up(f.nx, rows));

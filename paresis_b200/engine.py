@@ -83,6 +83,17 @@ class InsaneValues(Exception):
     pass
 
 
+def _on_own_device(method):
+    """Library calls launch on the CURRENT device: make the engine's device current for the duration of the call."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class ImageFormation:
     """Owns the scratch buffers of one GPU and runs membrane positions one after another."""
 
@@ -123,6 +134,7 @@ class ImageFormation:
                 self._kernels[key] = torch.as_tensor(hm.gaussian_1d(sigma), device=self.device, dtype=torch.float32)
         return self._kernels[key]
 
+    @_on_own_device
     def detect(self, image, fwhm, psf_sigma, sequence, out):
         """Detector.detection (Detector.py:79-119): device image -> ``out`` (device, detector dims)."""
         src = self._gauss(fwhm / 2.355) if fwhm != 0 else None
@@ -254,6 +266,7 @@ class ImageFormation:
         """Poisson stream id of a position; image k of bin b draws from sequence + 4b + k."""
         return (sequence_base + point_num) << 16
 
+    @_on_own_device
     def compute_rt(self, scene, point_num, want_displacement=False, sequence_base=0, probe=None, want_mean=True,
                    defer=False):
         """Experiment.computeSampleAndReferenceImages_RT (Experiment.py:407-526) as one library
@@ -321,6 +334,7 @@ class ImageFormation:
                 c["work"] = torch.empty(raster_bytes, device=self.device, dtype=torch.uint8)
         return cache[:n_slots]
 
+    @_on_own_device
     def compute_rt_positions(self, scene, plan, offsets, points, sequence_base=0, n_slots=2, probe_label=None,
                              probe_events=None, want_means=True, buffers=None, per_launch=0):
         """``len(offsets)`` membrane positions in one library call (paresis_rt_run_positions): per
@@ -401,6 +415,7 @@ class ImageFormation:
                    firsts=firsts, buffers=buffers)
         return out
 
+    @_on_own_device
     def accumulate_rt(self, scene, point_num, indices):
         """The energies ``indices`` (all of ONE detector bin) of a position, without the detector:
         leaves the partial sums in ``self.acc`` and returns the per-energy means of the reference
@@ -445,6 +460,7 @@ class ImageFormation:
             self._vectors[key] = (torch.as_tensor(hx, device=self.device), torch.as_tensor(hy, device=self.device), phase)
         return self._vectors[key]
 
+    @_on_own_device
     def propagate(self, scene, wave_in, distance, energy, magnification, wave_out=None, intensity_acc=None):
         """Experiment.wavePropagation (Experiment.py:219-252) on device fields."""
         self._fresnel_setup()
@@ -452,6 +468,7 @@ class ImageFormation:
         # |.|^2 ignores the global phase; a returned field carries it (formed in fp64 on the host)
         self._plan.propagate(wave_in, hx, hy, phase if wave_out is not None else 1.0, wave_out, intensity_acc)
 
+    @_on_own_device
     def compute_fresnel(self, scene, point_num, sequence_base=0):
         """Experiment.computeSampleAndReferenceImages_Fresnel (Experiment.py:279-405)."""
         s = scene

@@ -29,7 +29,9 @@ def energies_of(indices, rank, world):
 def reduce_images(stack, owner=0, group=None):
     """Sum per-rank partial images onto ``owner`` (in place).  ``stack`` is any float tensor."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.reduce(stack, dst=owner, op=dist.ReduceOp.SUM, group=group)
+        # `owner` is a rank OF THE GROUP; dist.reduce wants the global rank
+        dst = dist.get_global_rank(group, owner) if group is not None else owner
+        dist.reduce(stack, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return stack
 
 
@@ -81,12 +83,19 @@ def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, seq
                     abi.poisson(partial[k], out[name][b], engine.seed, seq + k)
                 else:
                     out[name][b].copy_(partial[k])
+    # the reference's NaN / "insane values" guard (refractionFileNumba2.py:81-82) must fire whichever rank saw the bad
+    # value: the status flags travel with the means (one all_reduce), every rank clears its own and every rank raises
+    tail = torch.cat((means, engine.flag.to(torch.float64)))
+    engine.flag.zero_()
     if world > 1:
-        dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=group)
+    tail = tail.cpu().numpy()
+    if tail[-1] != 0:
+        from .engine import InsaneValues
+        raise InsaneValues("The calculated intensity refractive includes some nans or insane values")
     if rank != owner:
         return None
-    m = means.cpu().numpy()
+    m = tail[:-1]
     energies = np.array([e for e, _ in scene.spectrum])
     out["mean_energy"] = (float(np.dot(m, energies)), float(m.sum()))
-    engine.check_flag()
     return out

@@ -60,14 +60,24 @@ class Pending:
                                                 ctypes.c_void_p(tensor.data_ptr()), nbytes, abi._stream()),
                    "paresis_transfer_d2h")
         bytes_d2h += nbytes
+        # A Pending that is dropped without wait() (a membrane map nobody reads) must not hand its pinned buffer and its
+        # source tensor back to the allocators while the copy is in flight on the library's copy stream: wait, then recycle.
+        self._finalizer = weakref.finalize(self, _abandon, self._key, self.host, self.lane, self._src)
 
     def wait(self):
+        self._finalizer.detach()
         abi._check(abi.lib.paresis_transfer_wait(self.lane), "paresis_transfer_wait")
         self._src = None
         host, self.host = self.host, None
         arr = host.numpy()
         weakref.finalize(arr, _release, self._key, (host, self.lane))
         return arr
+
+
+def _abandon(key, host, lane, src):
+    abi.lib.paresis_transfer_wait(lane)
+    del src
+    _release(key, (host, lane))
 
 
 def fetch(tensor, dtype=None):

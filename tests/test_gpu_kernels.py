@@ -381,13 +381,13 @@ def test_poisson_statistics(abi):
 
 @pytest.fixture
 def tile_config(abi, request):
-    """0 = lean tile kernel (refract_lean.cuh, production), 1 = first tile kernel (refract_tile.cuh)."""
+    """0 = the tile kernel (refract_lean.cuh)."""
     abi.set_tuning(2, request.param)
     yield request.param
     abi.set_tuning(2, 0)
 
 
-@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+@pytest.mark.parametrize("tile_config", [0], indirect=True)
 @pytest.mark.parametrize("shape", [(130, 290), (300, 257), (40, 36), (517, 1030), (96, 2048)])
 def test_tile_hop_kernel_matches_direct_kernel(abi, shape, tile_config):
     """The fixed-point shared-memory tile kernels (intensity_scale given) against the fp32 direct-to-L2
@@ -433,7 +433,7 @@ def test_tile_hop_kernel_matches_direct_kernel(abi, shape, tile_config):
     assert int(flag.item()) & abi.FLAG_NONFINITE
 
 
-@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+@pytest.mark.parametrize("tile_config", [0], indirect=True)
 @pytest.mark.parametrize("n_extra", [2, 3])
 def test_tile_hop_kernels_with_three_and_four_layers(abi, tile_config, n_extra):
     """Membrane + 2 or 3 sample materials (the multi-material phantoms of createSampGeom.py:110-260): the tile
@@ -498,7 +498,7 @@ def test_tile_kernels_with_unaligned_images(abi):
         assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 5e-6
 
 
-@pytest.mark.parametrize("tile_config", [0, 1], indirect=True)
+@pytest.mark.parametrize("tile_config", [0], indirect=True)
 def test_tile_hop_kernel_cannot_overflow(abi, tile_config):
     """Every ray of a tile focused into ONE cell (a lens): the fixed-point tile holds it (rays per tile x
     brightest fixed-point ray < 2^32) and the image gets the exact sum."""
