@@ -10,11 +10,21 @@ blur, binning and Poisson noise included.  Workload = BASELINE.json configs[1]: 
 oversampled grid, monochromatic 52 keV, 20 membrane positions, ray-tracing refraction model,
 detector PSF 1.2 px + Poisson noise (experiment "B200_2048_mono" of the shipped XML).
 
-One step = one 20-position job.  `value` is measured with all inputs resident in HBM
-(sphere list, sample map); `e2e` runs the same job through the drop-in Python API
-(Experiment.getMyGeometry + computeSampleAndReferenceImages_RT, numpy results on the host,
-membrane map copied back as main.py:99 does).  N > 1: one process per GPU (torchrun), each rank
-its own 20 positions, no data-path collective (positions are independent) -> weak scaling.
+One step = JOBS_PER_STEP (40) jobs of 20 membrane positions each = 800 image-sets, so that the timed region of the
+default run lasts seconds, not milliseconds (a sustained measurement: clocks and power settle).  `value` is measured
+with all inputs resident in HBM (sphere field, sample map); `e2e` runs 20-position jobs through the drop-in Python API
+(Experiment.getMyGeometry + computeSampleAndReferenceImages_RT, numpy results on the host, membrane map copied back as
+main.py:99 does) and is quoted next to the platform's device->host ceiling measured in the same run (`e2e.d2h_ceiling`).
+N > 1: one process per GPU (torchrun), each rank its own positions, no data-path collective for this workload
+(positions are independent) -> weak scaling.
+
+The same line carries, measured live in the same run:
+  `energy_sharded` -- BASELINE.json configs[2] (4096^2, 64 energies, 20 positions): the spectrum of every position is
+      dealt round-robin over the N ranks, each rank accumulates its energies, applies the linear part of the detector and
+      ONE NCCL reduce per detector bin sums the detector-resolution partials on the owner, which draws the Poisson noise
+      (paresis_b200/shard.py; Experiment.py:482-483, :501-521).  Strong scaling: the job is fixed, N splits it.
+  `grid_8192` (N = 1) -- BASELINE.json configs[4] sub-sample (8192^2, 8 of the 128 energies x 4 positions): throughput
+      and per-kernel roofline fractions at a grid whose working set does NOT fit the 126 MB L2.
 
 At N = 1 the line also carries `splat`: BASELINE.json's second figure, the stand-alone refraction splat
 (`paresis_splat`, 16 algorithmic bytes per study pixel) timed live on a membrane's displacement field at 2048^2 and
@@ -39,6 +49,8 @@ sys.path.insert(0, ROOT)
 
 EXPERIMENT = "B200_2048_mono"
 POSITIONS = 20
+JOBS_PER_STEP = 40      # a timed step = 40 jobs x 20 positions (a job is one paresis_rt_run_positions call)
+E2E_JOBS_PER_STEP = 5   # an end-to-end step = 5 jobs x 20 positions through the Python API
 METRIC = "speckle_image_sets_per_s"
 UNIT = "image-sets/s"
 WORKLOAD = "2048^2 grid (detector 1024^2 x os 2), mono 52 keV, 20 membrane positions, RayT, PSF 1.2 px + Poisson"
@@ -50,13 +62,13 @@ ALG_BYTES = {
     "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
     "detect": lambda n, det: 2 * (4.0 * n + 4.0 * det),       # sample + reference images in one launch: read, write counts
 }
-SLOTS = 4   # scratch sets; with PER_LAUNCH > 1 that many positions share each kernel launch (blockIdx.z), else they run on SLOTS streams
-PER_LAUNCH = 4
+SLOTS = 3        # positions in flight (paresis_rt_run_positions deals them over this many streams)
+PER_LAUNCH = 0   # > 1: that many positions share each kernel launch (blockIdx.z) instead; measured no faster
 
 
 def config_dict(**extra):
-    c = {"workload": WORKLOAD, "experiment": EXPERIMENT, "positions_per_step": POSITIONS, "grid": 2048,
-         "energies": 1, "model": "RayT"}
+    c = {"workload": WORKLOAD, "experiment": EXPERIMENT, "positions_per_step": POSITIONS * JOBS_PER_STEP, "positions_per_job": POSITIONS,
+         "grid": 2048, "energies": 1, "model": "RayT"}
     c.update(extra)
     return c
 
@@ -295,8 +307,10 @@ def run_gpu(args):
     # ---- timed region: device-resident job
     sampler = ClockSampler(local)
     sampler.start()
+    jobs = args.jobs_per_step
     for w in range(args.warmup):
-        device_job(1000 + w)
+        for jb in range(jobs):
+            device_job(100_000 + w * jobs + jb)
     barrier()
     sampler.mark()
     launches0 = abi.launches
@@ -305,8 +319,16 @@ def run_gpu(args):
     for s in range(args.steps):
         flush.zero_()                                       # L2 flush between timed steps (not timed)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); device_job(s, dominant, k_events); e1.record()
+        e0.record()
+        for jb in range(jobs):                              # one probed position per step, in its first job
+            if jb == 0:
+                device_job(s * jobs, dominant, k_events)
+            else:
+                device_job(s * jobs + jb)
+        e1.record()
         step_events.append((e0, e1))
+        if s % 8 == 7:
+            torch.cuda.synchronize()                        # bound the host's lead over the GPU (event / launch queues)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -318,7 +340,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s = float(t.item())
-    value = world * POSITIONS * args.steps / dev_s
+    value = world * POSITIONS * jobs * args.steps / dev_s
 
     # ---- e2e through the public API (host results)
     for w in range(max(1, min(args.warmup, 2))):
@@ -327,14 +349,20 @@ def run_gpu(args):
     t0 = time.perf_counter()
     h2d = d2h = 0
     for s in range(args.steps):
-        h2d, d2h = api_job(s)
+        h2d = d2h = 0
+        for jb in range(E2E_JOBS_PER_STEP):
+            a, b = api_job(s * E2E_JOBS_PER_STEP + jb)
+            h2d += a; d2h += b
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * POSITIONS * args.steps / float(t.item())
-    h2d += POSITIONS * 3 * 2 * 8          # the per-layer membrane offsets travel as kernel arguments
+    e2e_value = world * POSITIONS * E2E_JOBS_PER_STEP * args.steps / float(t.item())
+    h2d += E2E_JOBS_PER_STEP * POSITIONS * 3 * 2 * 8          # the per-layer membrane offsets travel as kernel arguments
+    ceiling = d2h_ceiling(torch, dist, world)
+    e2e_gbs = e2e_value * (d2h / (E2E_JOBS_PER_STEP * POSITIONS)) / 1e9          # whole-job device->host rate of the e2e run
+    sharded = energy_sharded(args, torch, dist, shim, geometry, abi, rank, world, ws)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -359,7 +387,12 @@ def run_gpu(args):
                                   host_cpus_bound=len(bound) if bound else None),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                    "pinned_buffers_allocated": transfer.pinned_allocs},
+                    "positions_per_step": E2E_JOBS_PER_STEP * POSITIONS, "pinned_buffers_allocated": transfer.pinned_allocs,
+                    "d2h_gbs": e2e_gbs, "d2h_ceiling": ceiling, "frac_of_d2h_ceiling": e2e_gbs / ceiling["aggregate_gbs"],
+                    "note": "results are float64 images + the float32 membrane map (main.py:99) in pinned host memory: "
+                            "the run is bound by the device->host link, whose ceiling is measured here with plain "
+                            "cudaMemcpyAsync copies of 64 MiB buffers on all ranks at once"},
+            "energy_sharded": sharded,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -370,6 +403,7 @@ def run_gpu(args):
         }
         if world == 1:
             line["splat"] = splat_roofline(abi, geometry, exp, torch, flush, peak)
+            line["grid_8192"] = grid_8192(args, torch, shim, geometry, abi, ws, peak, flush)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
@@ -419,6 +453,166 @@ def splat_roofline(abi, geometry, exp, torch, flush, peak):
     return out
 
 
+def d2h_ceiling(torch, dist, world, mib=64, reps=24):
+    """What the platform gives a plain device->host copy: one cudaMemcpyAsync per 64 MiB buffer into pinned memory, all
+    ranks at the same time (the ranks of a node share the host's PCIe root / memory bandwidth)."""
+    n = mib * 1024 * 1024
+    dev = torch.empty(n, device="cuda", dtype=torch.uint8)
+    host = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for h in host:
+        h.copy_(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(reps):
+        host[k & 1].copy_(dev, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = reps * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbs, gbs], device="cuda", dtype=torch.float64)
+    if world > 1:
+        lo = t[1:].clone()
+        dist.all_reduce(t[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        t[1] = lo[0]
+    return {"aggregate_gbs": float(t[0].item()), "min_rank_gbs": float(t[1].item()), "ranks": world, "buffer_mib": mib}
+
+
+def energy_sharded(args, torch, dist, shim, geometry, abi, rank, world, ws):
+    """BASELINE.json configs[2]: 4096^2, 64 energies, 20 membrane positions, the spectrum of each position sharded over
+    the ranks and summed with ONE NCCL reduce per detector bin (paresis_b200/shard.py).  Strong scaling."""
+    if args.skip_extras:
+        return None
+    import contextlib
+    import io
+    from paresis_b200 import shard
+    positions, reps = 20, 2
+    with contextlib.redirect_stdout(io.StringIO()):
+        exp = shim.Experiment(dict(experimentName="B200_4096_poly64", filepath=os.path.join(ws, "out", ""), overSampling=2,
+                                   nbExpPoints=positions, simulation_type="RayT", expID="shard", seed=99))
+    n = int(exp.exp_dict["studyDimensions"][0])
+    det = int(exp.myDetector.det_param["myDimensions"][0])
+    eng, mem = exp._get_engine(), exp.myMembrane
+    exp.myDetector.det_param["myBinsThersholds"] = []
+    thresholds = list(exp._open_bins(0))
+    reduce_events = []
+
+    def job(rep):
+        np.random.seed(777 + rep)                                # the same membrane positions on every rank
+        with contextlib.redirect_stdout(io.StringIO()):
+            for point in range(positions):
+                # the membrane of this position, cut on every rank (no host copy of the map: nobody saves it here)
+                mem.myGeometry, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, point, mem.myPMMAThickness)
+                scene = exp._scene(thresholds)
+                shard.compute_rt_energy_sharded(eng, scene, point, owner=0, sequence_base=rep * positions,
+                                                reduce_events=reduce_events if rep >= 0 else None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    job(-1)
+    barrier()
+    launches0 = abi.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for rep in range(reps):
+        job(rep)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    red_ms = sum(a.elapsed_time(b) for a, b in reduce_events)
+    t = torch.tensor([ms, red_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, red_ms = float(t[0].item()), float(t[1].item())
+    n_red = len(reduce_events)
+    images_first, images_rest = 4, 2
+    bytes_per_reduce = det * det * 4 * images_rest
+    return {"workload": "4096^2 grid, 64 energies (20..83 keV), 20 membrane positions, RayT, one detector bin; energies round-robin over ranks",
+            "experiment": "B200_4096_poly64", "scaling": "strong", "n_gpus": world, "metric": METRIC, "unit": UNIT,
+            "value": reps * positions / (ms * 1e-3), "ms_per_position": ms / (reps * positions),
+            "energies_per_rank": [len(shard.energies_of(list(range(len(exp.mySource.mySpectrum))), r, world)) for r in range(world)],
+            "collective": {"op": "ncclReduce(sum, fp32) of detector-resolution partial images, one per detector bin and position" if world > 1 else "none (one rank)",
+                           "reduces": n_red, "bytes_per_reduce": bytes_per_reduce, "bytes_per_reduce_first_position": det * det * 4 * images_first,
+                           "reduce_ms_total": red_ms, "reduce_ms_per_position": red_ms / (reps * positions),
+                           "reduce_share_of_time": red_ms / ms if ms > 0 else None,
+                           "effective_gbs": (n_red * bytes_per_reduce / (red_ms * 1e-3) / 1e9) if red_ms > 0 and world > 1 else None,
+                           "note": "CUDA events around dist.reduce on the compute stream: includes waiting for the slowest rank"},
+            "gpu_launches": int(abi.launches - launches0), "timing": "CUDA events around %d x %d positions, max over ranks" % (reps, positions)}
+
+
+def grid_8192(args, torch, shim, geometry, abi, ws, peak, flush):
+    """BASELINE.json configs[4] sub-sample on one GPU: 8192^2, 8 of the 128 energies x 4 membrane positions, through the same
+    many-positions call as the headline; per-kernel CUDA-event times and roofline fractions at a DRAM-resident grid."""
+    if args.skip_extras:
+        return None
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        exp = shim.Experiment(dict(experimentName="B200_8192_poly128", filepath=os.path.join(ws, "out", ""), overSampling=2,
+                                   nbExpPoints=4, simulation_type="RayT", expID="g8k", seed=5))
+    keep = list(range(0, 128, 16))
+    exp.mySource.mySpectrum = [exp.mySource.mySpectrum[i] for i in keep]
+    n = int(exp.exp_dict["studyDimensions"][0])
+    det = int(exp.myDetector.det_param["myDimensions"][0])
+    eng, mem = exp._get_engine(), exp.myMembrane
+    exp.myDetector.det_param["myBinsThersholds"] = []
+    thresholds = list(exp._open_bins(0))
+    scene = exp._scene(thresholds, per_position_membrane=True)
+    plan = geometry.MembranePlan(mem, n, n, mem.membranePixelSize)
+    points = [1, 2, 3, 4]
+    state = {"buffers": None}
+
+    def job(step, probe_label=None, events=None, slots=2):
+        np.random.seed(4000 + step)
+        offsets = [plan.draw_offsets() for _ in points]
+        pe = None
+        if probe_label is not None:
+            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in points]
+            events.extend(pe)
+        with abi.on_stream():
+            res = eng.compute_rt_positions(scene, plan, offsets, points, sequence_base=step * 8, n_slots=slots,
+                                           probe_label=probe_label, probe_events=pe, buffers=state["buffers"])
+        state["buffers"] = res["buffers"]
+
+    job(-1)
+    torch.cuda.synchronize()
+    eng.check_flag()
+    times = []
+    for step in range(3):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); job(step); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    kernels = {}
+    px, dpx, n_e = float(n) * n, float(det) * det, len(keep)
+    # algorithmic bytes per launch; the object hop of a polychromatic bin runs 4 energies per launch (12 + 8/G B/px per energy)
+    alg = {"raster_spheres": 4.0 * px, "refract_membrane_hop": 8.0 * px, "refract_sample_ref_hop": (12.0 * 4 + 8.0) * px,
+           "detect": 2 * (4.0 * px + 4.0 * dpx)}
+    for k, label in enumerate(("raster_spheres", "refract_membrane_hop", "refract_sample_ref_hop", "detect")):
+        ev = []
+        job(-3 - k, label, ev, slots=1)
+        torch.cuda.synchronize()
+        v = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        gbs = alg[label] / (v * 1e-3) / 1e9
+        kernels[label] = {"ms_per_launch": v, "alg_bytes_per_launch": alg[label], "achieved_gbs": gbs, "frac": gbs / peak}
+    del state, eng, exp
+    geometry.drop_device_tables()
+    torch.cuda.empty_cache()
+    return {"workload": "8192^2 grid, 8 of the 128 energies (20, 28, ... 76 keV) x 4 membrane positions, RayT, one detector bin",
+            "experiment": "B200_8192_poly128", "positions_per_s": len(points) / (ms * 1e-3), "ms_per_position": ms / len(points),
+            "ms_per_energy_and_position": ms / len(points) / n_e, "kernels": kernels, "peak_gbs": peak,
+            "note": "per-kernel rows: CUDA events around the first launch of that kind in each position, positions one at a time; "
+                    "the object hop is the 4-energy group kernel of a polychromatic bin"}
+
+
 def profile_kernels(abi, job, torch):
     """Untimed jobs, one position in flight, with CUDA events around one kernel class at a time (the probe of
     paresis_rt_run_positions): ms per launch and per 20-position step."""
@@ -443,6 +637,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=SLOTS, help="membrane positions in flight on the GPU")
+    ap.add_argument("--jobs-per-step", type=int, default=JOBS_PER_STEP, help="20-position jobs per timed step")
+    ap.add_argument("--skip-extras", action="store_true", help="headline only: no splat / 8192^2 / energy-sharded sections")
     ap.add_argument("--per-launch", type=int, default=PER_LAUNCH, help="membrane positions per kernel launch (0: one launch per position, on --slots streams)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -45,11 +45,12 @@ def combine_means(values, indices, n_total, group=None):
     return full
 
 
-def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, sequence_base=0):
+def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, sequence_base=0, reduce_events=None):
     """One membrane position with the spectrum spread over the ranks of ``group``.
 
     Every rank calls this with the same scene.  Returns, on ``owner``, the dict that
-    ``ImageFormation.compute_rt`` returns (device tensors + mean_energy); None elsewhere."""
+    ``ImageFormation.compute_rt`` returns (device tensors + mean_energy); None elsewhere.
+    ``reduce_events``: a list that receives one (start, end) CUDA event pair per NCCL reduction (bench.py)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     first = point_num == 0
@@ -75,7 +76,14 @@ def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, seq
                 # the linear part of the detector before the exchange: detector-resolution images travel
                 abi.detect_counts(engine.acc[name], engine.os, engine.det_x, engine.det_y, src, psf, engine.work,
                                   partial[k], False)
-        reduce_images(partial, owner, group)
+        if reduce_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reduce_images(partial, owner, group)
+            e1.record()
+            reduce_events.append((e0, e1))
+        else:
+            reduce_images(partial, owner, group)
         if rank == owner:
             seq = engine.sequence(point_num, sequence_base) + 4 * b
             for k, name in enumerate(IMAGES[:count]):
