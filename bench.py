@@ -404,6 +404,7 @@ def run_gpu(args):
         if world == 1:
             line["splat"] = splat_roofline(abi, geometry, exp, torch, flush, peak)
             line["grid_8192"] = grid_8192(args, torch, shim, geometry, abi, ws, peak, flush)
+            line["fresnel"] = fresnel_section(args, torch, shim, geometry, ws, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
@@ -611,6 +612,46 @@ def grid_8192(args, torch, shim, geometry, abi, ws, peak, flush):
             "ms_per_energy_and_position": ms / len(points) / n_e, "kernels": kernels, "peak_gbs": peak,
             "note": "per-kernel rows: CUDA events around the first launch of that kind in each position, positions one at a time; "
                     "the object hop is the 4-energy group kernel of a polychromatic bin"}
+
+
+def fresnel_section(args, torch, shim, geometry, ws, peak):
+    """BASELINE.json configs[3]: the Fresnel-propagator model (Experiment.py:279-405, wavePropagation :219-252) at 4096^2 and
+    8192^2, device time per membrane position (three propagations: reference beam, membrane->object, object->detector; the
+    first two share their forward transform).  Roofline entry of the propagation: >= 64 B per padded pixel (two 2-D
+    transforms, each two passes of read + write of complex64) against what it takes -- the transforms are cuFFT at the
+    reference's (N + 30)^2 size, 4126 = 2 x 2063 and 8222 = 2 x 4111: Bluestein (profiles/r02_fresnel_launches.txt)."""
+    if args.skip_extras:
+        return None
+    import contextlib
+    import io
+    out = {"alg_bytes_per_padded_pixel_per_propagation": 64, "propagations_per_position": 3, "forward_transforms_per_position": 2,
+           "peak_gbs": peak, "grids": {}}
+    for n in (4096, 8192):
+        with contextlib.redirect_stdout(io.StringIO()):
+            exp = shim.Experiment(dict(experimentName="B200_%d_mono" % n, filepath=os.path.join(ws, "out", ""), overSampling=2,
+                                       nbExpPoints=4, simulation_type="Fresnel", expID="fr", seed=3))
+        eng, mem = exp._get_engine(), exp.myMembrane
+        exp.myDetector.det_param["myBinsThersholds"] = []
+        thresholds = list(exp._open_bins(0))
+        np.random.seed(n)
+        times = []
+        for point in (1, 2, 3, 4):
+            mem.myGeometry, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, point, mem.myPMMAThickness)
+            scene = exp._scene(thresholds)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.compute_fresnel(scene, point); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[1:]))
+        padded = float(n + 30) ** 2
+        gbs = 3 * 64.0 * padded / (ms * 1e-3) / 1e9
+        out["grids"][str(n)] = {"ms_per_position": ms, "positions_per_s": 1e3 / ms, "fft_size": n + 30,
+                                "achieved_gbs": gbs, "frac": gbs / peak}
+        del eng, exp, scene
+        geometry.drop_device_tables()
+        torch.cuda.empty_cache()
+    return out
 
 
 def profile_kernels(abi, job, torch):

@@ -311,6 +311,14 @@ int paresis_fresnel_propagate(paresis_fresnel_plan* plan, const paresis_c32* wav
                               const paresis_c32* hx, const paresis_c32* hy, paresis_c32 phase,
                               paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);
 
+/* Several propagations of the SAME field over different distances (Experiment.py:340-341 and :349 both start from the
+ * wave behind the membrane): paresis_fresnel_spectrum keeps fft2(np.pad(wave, margin, 'reflect')) inside the plan
+ * (a second padded buffer, allocated on first use), paresis_fresnel_from_spectrum applies one transfer function to it,
+ * transforms back, crops and delivers like paresis_fresnel_propagate.  One forward transform saved per extra distance. */
+int paresis_fresnel_spectrum(paresis_fresnel_plan* plan, const paresis_c32* wave_in, paresis_stream stream);
+int paresis_fresnel_from_spectrum(paresis_fresnel_plan* plan, const paresis_c32* hx, const paresis_c32* hy, paresis_c32 phase,
+                                  paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);
+
 /* ---------------------------------------------------------------------------------------
  * Detector
  * ------------------------------------------------------------------------------------- */

@@ -24,7 +24,7 @@ REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
 EXPORTS = (
     "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
-    "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_detect_work_floats", "paresis_detect",
+    "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_fresnel_spectrum", "paresis_fresnel_from_spectrum", "paresis_detect_work_floats", "paresis_detect",
     "paresis_detect_counts", "paresis_detect_counts_multi",
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
@@ -128,6 +128,8 @@ def _load():
         "paresis_fresnel_plan_create": [ci, ci, ci, ctypes.POINTER(vp)],
         "paresis_fresnel_plan_destroy": [vp],
         "paresis_fresnel_propagate": [vp, vp, vp, vp, C32, vp, vp, vp],
+        "paresis_fresnel_spectrum": [vp, vp, vp],
+        "paresis_fresnel_from_spectrum": [vp, vp, vp, C32, vp, vp, vp],
         "paresis_detect": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, vp],
         "paresis_detect_counts": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, ci, u64, u64, vp],
         "paresis_detect_counts_multi": [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u64), ci, ci, ci, ci, ci, ci, vp, ci,
@@ -418,6 +420,18 @@ class FresnelPlan:
                                              _ptr(intensity_acc, torch.float32), _stream()),
                "paresis_fresnel_propagate")
         _count(5)
+
+    def spectrum(self, wave_in):
+        """fft2(pad(wave_in)) kept inside the plan for from_spectrum()."""
+        _check(lib.paresis_fresnel_spectrum(self._h, _ptr(wave_in, torch.complex64), _stream()), "paresis_fresnel_spectrum")
+        _count(2)
+
+    def from_spectrum(self, hx, hy, phase=1.0 + 0.0j, wave_out=None, intensity_acc=None):
+        ph = C32(float(np.real(phase)), float(np.imag(phase)))
+        _check(lib.paresis_fresnel_from_spectrum(self._h, _ptr(hx, torch.complex64), _ptr(hy, torch.complex64), ph,
+                                                 _ptr(wave_out, torch.complex64), _ptr(intensity_acc, torch.float32), _stream()),
+               "paresis_fresnel_from_spectrum")
+        _count(3)
 
     def close(self):
         if self._h:

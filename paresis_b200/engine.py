@@ -491,10 +491,14 @@ class ImageFormation:
             # after the membrane (:338); uniform layers: attenuation folded in, constant phase dropped
             abi.transmit_wave(None, amp * np.exp(-k * mem_ub), [t for t, _, _ in mem_maps],
                               [k * b for _, _, b in mem_maps], [k * d for _, d, _ in mem_maps], w_a)
+            # Both beams start from the wave behind the membrane: its reflect-pad + forward FFT is done once.
             # reference beam: membrane -> detector in one hop (:349, :354)
-            self.propagate(s, w_a, s.d3 + s.d2, energy, s.magnification, intensity_acc=self.acc["reference"])
+            self._plan.spectrum(w_a)
+            hx, hy, phase = self._transfer(s, s.d3 + s.d2, energy, s.magnification)
+            self._plan.from_spectrum(hx, hy, 1.0, None, self.acc["reference"])
             # sample beam: membrane -> object (:340-341), through the sample (:344), -> detector (:348)
-            self.propagate(s, w_a, s.d2, energy, mag_mem_obj, wave_out=w_b)
+            hx, hy, phase = self._transfer(s, s.d2, energy, mag_mem_obj)
+            self._plan.from_spectrum(hx, hy, phase, w_b, None)
             abi.transmit_wave(w_b, 0.0, [t for t, _, _ in smp_maps], [k * b for _, _, b in smp_maps],
                               [k * d for _, d, _ in smp_maps], w_b)
             self.propagate(s, w_b, s.d3, energy, s.magnification, intensity_acc=self.acc["sample"])
