@@ -8,7 +8,9 @@ messages and the report file.  The per-energy image-formation loops
 Extensions read from ``exp_dict`` when present (the reference ignores unknown keys):
 ``poissonNoise`` (bool, default True), ``seed`` (int, default wall clock like Detector.py:113),
 ``returnDisplacement`` (bool, default True: Dx/Dy of point 0 are copied back), ``resultDtype`` ("float64" as
-upstream, or "float32": counts are exact in float32 and cross PCIe at half the size -- what main.py saves anyway).
+upstream, or "float32": counts are exact in float32 and cross PCIe at half the size -- what main.py saves anyway),
+``membraneAhead`` (bool, default True: the next position's membrane map is cut and copied speculatively while this
+position's images travel; see geometry.speculate_next_membrane).
 """
 import time
 
@@ -254,11 +256,21 @@ class Experiment:
                                                  seed=det.seed, poisson=det.poissonNoise)
         return self._engine
 
-    def _finish(self, res, scene=None):
+    def _membrane_ahead(self, pointNum=None):
+        """Start the next position's membrane map while this position's images travel (geometry.speculate_next_membrane)."""
+        mem = self.myMembrane
+        if getattr(mem, "myGeometryFunction", "") == "getMembraneSegmentedFromFile" and self.exp_dict.get("membraneAhead", True):
+            d = self.exp_dict
+            geometry.speculate_next_membrane(mem, d['studyDimensions'][0], d['studyDimensions'][1], mem.membranePixelSize,
+                                             mem.myPMMAThickness)
+
+    def _finish(self, res, scene=None, ahead=False):
         """Device images -> the float64 [nbins, dimX, dimY] arrays the reference returns; images that were
         not computed (propagation / white beyond point 0) are zeros, as upstream (Experiment.py:433-434)."""
         dtype = torch.float32 if str(self.exp_dict.get("resultDtype", "float64")) == "float32" else torch.float64
         images = transfer.Pending(res["_stack"], dtype)            # one cast + one PCIe copy for all images
+        if ahead:
+            self._membrane_ahead()                                 # queued behind the images: the link does not idle
         if "aux" in res:
             # deferred bookkeeping: the per-energy sums and the status flag ride behind the images
             aux = transfer.Pending(res["aux"])
@@ -316,7 +328,7 @@ class Experiment:
         scene = self._scene(thresholds)
         try:
             res = eng.compute_rt(scene, pointNum, want_displacement=want_d, defer=True)
-            out = self._finish(res, scene)
+            out = self._finish(res, scene, ahead=True)
         except engine.InsaneValues as exc:
             raise Exception(str(exc))
         if want_d:

@@ -89,6 +89,8 @@ FIELD_BYTES_LIMIT = 16 << 30   # beyond this the membrane is rasterised per posi
 
 def drop_device_tables():
     """Forget the device copies (the next position uploads the sphere list again)."""
+    global _speculated
+    _speculated = None
     _device_tables.clear()
     _device_fields.clear()
 
@@ -189,20 +191,53 @@ def _plan(sample, dim_x, dim_y, pix):
     return plan
 
 
+_speculated = None     # the next position's map, cut ahead of time: dict(plan, offsets, geom)
+
+
+def _cut_membrane(plan, offsets, pix, grains):
+    field = plan.field()
+    if field is not None:
+        abi.membrane_from_field(field, offsets, plan.margin, plan.dim_x, plan.dim_y, grains)
+    else:
+        abi.raster_spheres(plan.table, pix, offsets, plan.dim_x, plan.dim_y, plan.margin, grains)
+
+
+def speculate_next_membrane(sample, dim_x, dim_y, pix, support_um):
+    """Cut the membrane map the NEXT getMembraneSegmentedFromFile call will ask for, and start its copy to the host, now.
+
+    The per-position flow of main.py (:63-110) is strictly serial: the next position's map is only requested once this
+    position's images are on the host, so the device->host link idles through the host's turn-around and the cut
+    kernel.  The next offsets are the next ``np.random.randint`` draws (getMembraneFromFile.py:139-140): they are drawn
+    here from a COPY of numpy's global state (the caller's stream is left untouched); when the real call draws the
+    same numbers -- nobody re-seeded or drew in between -- the map and its copy are already under way; otherwise the
+    speculation is dropped and the map is cut as usual.  Results are identical either way."""
+    global _speculated
+    plan = _plan(sample, dim_x, dim_y, pix)
+    state = np.random.get_state()
+    offsets = plan.draw_offsets()
+    np.random.set_state(state)
+    grains = torch.empty((plan.dim_x, plan.dim_y), device=device(), dtype=torch.float32)
+    _cut_membrane(plan, offsets, pix, grains)
+    geom = DeviceGeometry([grains, support_um * 1e-6], (plan.dim_x, plan.dim_y))
+    geom.prefetch(0)
+    _speculated = dict(plan=plan, offsets=offsets, geom=geom, support=support_um)
+
+
 def membrane_segmented(sample, dim_x, dim_y, pix, point_num, support_um, out=None, prefetch=False):
     """getMembraneSegmentedFromFile (Samples/getMembraneFromFile.py:60-171)."""
+    global _speculated
     plan = _plan(sample, dim_x, dim_y, pix)
     offsets = plan.draw_offsets()
     dim_x, dim_y = plan.dim_x, plan.dim_y
-    grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)
-    field = plan.field()
-    if field is not None:
-        abi.membrane_from_field(field, offsets, plan.margin, dim_x, dim_y, grains)
-    else:
-        abi.raster_spheres(plan.table, pix, offsets, dim_x, dim_y, plan.margin, grains)
     params = {'Average sphere radius': (sample.myMeanSphereRadius, 'um'),
               'Number of layers': (sample.myNbOfLayers, ''),
               'Support total thickness': (support_um, 'um')}
+    ahead, _speculated = _speculated, None
+    if (ahead is not None and out is None and prefetch and ahead["plan"] is plan and ahead["offsets"] == offsets
+            and ahead["support"] == support_um):
+        return ahead["geom"], params
+    grains = out if out is not None else torch.empty((dim_x, dim_y), device=device(), dtype=torch.float32)
+    _cut_membrane(plan, offsets, pix, grains)
     geom = DeviceGeometry([grains, support_um * 1e-6], (dim_x, dim_y))
     if prefetch:
         geom.prefetch(0)      # main.py:99 saves this map: start the copy now, it overlaps the image formation
