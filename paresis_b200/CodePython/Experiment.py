@@ -269,11 +269,11 @@ class Experiment:
         not computed (propagation / white beyond point 0) are zeros, as upstream (Experiment.py:433-434)."""
         dtype = torch.float32 if str(self.exp_dict.get("resultDtype", "float64")) == "float32" else torch.float64
         images = transfer.Pending(res["_stack"], dtype)            # one cast + one PCIe copy for all images
-        if ahead:
-            self._membrane_ahead()                                 # queued behind the images: the link does not idle
         if "aux" in res:
             # deferred bookkeeping: the per-energy sums and the status flag ride behind the images
             aux = transfer.Pending(res["aux"])
+            if ahead:
+                self._membrane_ahead()                             # queued behind the images and the sums: the link does not idle
             host = images.wait()
             num, den = self._get_engine().finish_deferred(scene, aux.wait())
         else:

@@ -304,7 +304,14 @@ def test_reference_main_script_runs_unmodified(golden, tmp_path, monkeypatch):
     got = open(results / report[0]).read().replace(exp_id, "<ID>")
     strip = lambda t: re.sub(r"Entire computing time: [0-9.e+-]+s", "Entire computing time: Xs", t)
     got_lines, want_lines = strip(got).splitlines(), strip(str(g["report"])).splitlines()
-    assert got_lines == want_lines
+    assert len(got_lines) == len(want_lines)
+    for a, b in zip(got_lines, want_lines):
+        if a.strip().startswith("meanEnergy:"):
+            # (m * E) / m in floating point: 52.0 or 52.00000000000001 depending on the last bit of the image mean m
+            assert b.strip().startswith("meanEnergy:") and a.split()[-1] == b.split()[-1] == "keV"
+            assert abs(float(a.split()[1]) / float(b.split()[1]) - 1) < 1e-12
+        else:
+            assert a == b
 
 
 @pytest.mark.parametrize("model", ["RayT", "Fresnel"])
