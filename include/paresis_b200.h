@@ -46,6 +46,9 @@ const char* paresis_last_error(void);
  * (0 = one REDG per deposit, 2 = warp/register aggregated, default); key 1: source rows per warp
  * (0 = automatic). */
 int paresis_set_tuning(int key, int value);
+/* Frees the library's cached per-device scratch (the ray lists of the strip kernels: up to 16 bytes per study pixel and
+ * beam, kept between calls so that a call allocates nothing).  Safe at any time; the next call allocates again. */
+int paresis_trim(void);
 
 /* ---------------------------------------------------------------------------------------
  * Refraction model (ray tracing)

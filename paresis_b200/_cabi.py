@@ -22,7 +22,7 @@ REFRACTION_MARGIN = 15   # refractionFileNumba2.py:50
 REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
 
 EXPORTS = (
-    "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
+    "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_trim", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
     "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_fresnel_spectrum", "paresis_fresnel_from_spectrum", "paresis_detect_work_floats", "paresis_detect",
     "paresis_detect_counts", "paresis_detect_counts_multi",

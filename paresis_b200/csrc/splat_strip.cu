@@ -13,6 +13,7 @@
 // that all blocks agree on which rays are tile rays.  Rays outside [2^-13, 2) of that scale, like rays that move
 // further than H = 12 pixels or touch the image border, go through make_ray() -- the reference's loop-frame rules --
 // in the drain launch.
+#include <mutex>
 #include <type_traits>
 
 #include "strip.cuh"
@@ -168,6 +169,16 @@ splat_drain_kernel(const uint4* __restrict__ far, const unsigned* __restrict__ f
     sp.finish();
 }
 
+int launch_splat_drain(const uint4* far, const unsigned* far_count, unsigned far_cap, unsigned n_slices, float* out, const Frame& f, int* flag,
+                       cudaStream_t s) {
+    splat_drain_kernel<<<(n_slices + 3) / 4, 128, 0, s>>>(far, far_count, far_cap, n_slices, out, f, flag);
+    PARESIS_LAUNCH_CHECK("splat_drain_kernel");
+    return PARESIS_OK;
+}
+
+bool splat_strip2_fits(const float* I, const float* Dx, const float* Dy, const float* out, const Frame& f);      // splat_strip2.cu
+int launch_splat_strip2(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, bool accumulate, cudaStream_t s);
+
 static DeviceSlots g_splat_slots[2];
 
 template <bool ACC>
@@ -196,28 +207,87 @@ static int launch_variant(const float* I, const float* Dx, const float* Dy, floa
 
 int launch_splat_strip(const float* I, const float* Dx, const float* Dy, float* out, const Frame& f, int* flag, bool accumulate,
                        cudaStream_t s) {
+    // aligned images: two source columns per thread (splat_strip2.cu); anything else: one column per thread (this file)
+    if (splat_strip2_fits(I, Dx, Dy, out, f)) return launch_splat_strip2(I, Dx, Dy, out, f, flag, accumulate, s);
     return accumulate ? launch_variant<true>(I, Dx, Dy, out, f, flag, s) : launch_variant<false>(I, Dx, Dy, out, f, flag, s);
 }
 
-// ---- stream-ordered scratch ------------------------------------------------------------------------------------
+// ---- scratch for the ray lists --------------------------------------------------------------------------------------
+// One cached block per device (the library's per-device workspace): it grows on demand and is handed from stream to
+// stream through an event, so a call costs no allocation and no synchronisation on the same stream.  A second call
+// while the block is out (another host thread) takes a stream-ordered allocation of its own.  paresis_trim() frees it.
+namespace {
+struct ScratchCache {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaStream_t last = nullptr;
+    cudaEvent_t released = nullptr;
+    bool out = false;
+};
+ScratchCache g_scratch[32];
+std::mutex g_scratch_lock;
+}  // namespace
+
 int strip_scratch_alloc(size_t bytes, void** ptr, cudaStream_t s) {
-    static bool pool_kept[32] = {false};
     int dev = 0;
     PARESIS_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 32 && !pool_kept[dev]) {
-        cudaMemPool_t pool;
-        PARESIS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long keep = ~0ull;                      // freed blocks stay in the pool: later calls do not touch the OS
-        PARESIS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_kept[dev] = true;
+    if (dev < 0 || dev >= 32) dev = 0;
+    if (bytes < 256) bytes = 256;
+    std::lock_guard<std::mutex> guard(g_scratch_lock);
+    ScratchCache& c = g_scratch[dev];
+    if (!c.out) {
+        if (c.ptr && c.bytes < bytes) {                 // too small: give it back in the order of its last user
+            PARESIS_CUDA(cudaFreeAsync(c.ptr, c.last));
+            c.ptr = nullptr;
+        }
+        if (!c.ptr) {
+            if (!c.released) PARESIS_CUDA(cudaEventCreateWithFlags(&c.released, cudaEventDisableTiming));
+            PARESIS_CUDA(cudaMallocAsync(&c.ptr, bytes, s));
+            c.bytes = bytes;
+        } else if (c.last != s) {
+            PARESIS_CUDA(cudaStreamWaitEvent(s, c.released, 0));
+        }
+        c.out = true;
+        c.last = s;
+        *ptr = c.ptr;
+        return PARESIS_OK;
     }
-    PARESIS_CUDA(cudaMallocAsync(ptr, bytes < 256 ? 256 : bytes, s));
+    PARESIS_CUDA(cudaMallocAsync(ptr, bytes, s));
     return PARESIS_OK;
 }
 
 int strip_scratch_free(void* ptr, cudaStream_t s) {
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    std::lock_guard<std::mutex> guard(g_scratch_lock);
+    ScratchCache& c = g_scratch[dev];
+    if (c.out && ptr == c.ptr) {
+        PARESIS_CUDA(cudaEventRecord(c.released, s));
+        c.last = s;
+        c.out = false;
+        return PARESIS_OK;
+    }
     PARESIS_CUDA(cudaFreeAsync(ptr, s));
     return PARESIS_OK;
 }
 
+int strip_scratch_trim() {
+    std::lock_guard<std::mutex> guard(g_scratch_lock);
+    for (int d = 0; d < 32; ++d) {
+        ScratchCache& c = g_scratch[d];
+        if (c.ptr && !c.out) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(d);
+            cudaFreeAsync(c.ptr, c.last);
+            cudaSetDevice(cur);
+            c.ptr = nullptr; c.bytes = 0;
+        }
+    }
+    return PARESIS_OK;
+}
+
 }  // namespace paresis
+
+extern "C" int paresis_trim(void) { return paresis::strip_scratch_trim(); }

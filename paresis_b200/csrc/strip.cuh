@@ -357,9 +357,10 @@ struct DeviceSlots {
     }
 };
 
-// Stream-ordered scratch for the ray lists (entries + one counter per block).  The library owns no long-lived
-// buffers for this: the pool keeps freed blocks, so after the first call this is a pointer bump.
+// Scratch for the ray lists (entries + one counter per warp): a per-device block cached inside the library, handed from
+// stream to stream through an event (splat_strip.cu).
 int strip_scratch_alloc(size_t bytes, void** ptr, cudaStream_t s);
 int strip_scratch_free(void* ptr, cudaStream_t s);
+int strip_scratch_trim();
 
 }  // namespace paresis
