@@ -180,16 +180,15 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
                 const float4 q = src[k];
                 in[4 * k] = q.x; in[4 * k + 1] = q.y; in[4 * k + 2] = q.z; in[4 * k + 3] = q.w;
             }
-            float4 r;
-            float* rr = reinterpret_cast<float*>(&r);
+            float r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float acc = 0.f;
 #pragma unroll
                 for (int f = 0; f < T::NP; ++f) acc = fmaf(P[f], in[k + f], acc);
-                rr[k] = acc;
+                r[k] = acc;
             }
-            *reinterpret_cast<float4*>(R3 + u * T::R3W + 4 * bq) = r;
+            *reinterpret_cast<float4*>(R3 + u * T::R3W + 4 * bq) = make_float4(r[0], r[1], r[2], r[3]);
         }
     }
     __syncthreads();

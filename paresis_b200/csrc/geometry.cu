@@ -137,27 +137,7 @@ raster_gather_kernel(const int* __restrict__ n_caps_all, const Cap* __restrict__
 // out[r][c] = sum over layers of field[ox_l + margin + r][oy_l + margin + c].
 // Window starts are arbitrary, so loads are scalar; a thread owns four columns 256 apart, which keeps every
 // load and store instruction of a warp on 32 consecutive floats.
-__global__ void __launch_bounds__(256)
-membrane_from_field_kernel(const float* __restrict__ field, int field_x, int field_y, LayerOffsets off, int n_layers, int margin,
-                           int dim_x, int dim_y, float* __restrict__ out) {
-    const int c0 = blockIdx.x * 1024 + threadIdx.x;
-    const int r = blockIdx.y;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int l = 0; l < n_layers; ++l) {
-        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c0;
-        if (fr < 0 || fr >= field_x) continue;
-        const float* src = field + (size_t)fr * field_y;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long f = fc + 256 * k;
-            if (c0 + 256 * k < dim_y && f >= 0 && f < field_y) acc[k] += __ldg(src + f);
-        }
-    }
-    float* o = out + (size_t)r * dim_y + c0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (c0 + 256 * k < dim_y) o[256 * k] = acc[k];
-}
+// (the kernel is membrane_from_field_batch_kernel, further down: one launch for up to 8 positions)
 
 __global__ void sphere_map_kernel(double rad, double scale_m, int dim_x, int dim_y, float* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,15 +313,9 @@ extern "C" int paresis_membrane_from_field(const float* field, int field_x, int 
         set_last_error("paresis_membrane_from_field: bad arguments (layers 1..%d)", MAX_MEMBRANE_LAYERS);
         return PARESIS_ERR_ARG;
     }
-    LayerOffsets off{};
-    for (int l = 0; l < n_layers; ++l) {
-        off.x[l] = offsets_host[2 * l];
-        off.y[l] = offsets_host[2 * l + 1];
-    }
-    membrane_from_field_kernel<<<dim3(div_up(dim_y, 1024), dim_x), 256, 0, (cudaStream_t)stream>>>(
-        field, field_x, field_y, off, n_layers, margin, dim_x, dim_y, thickness_out);
-    PARESIS_LAUNCH_CHECK("membrane_from_field_kernel");
-    return PARESIS_OK;
+    const int64_t* offs[1] = {offsets_host};
+    float* outs[1] = {thickness_out};
+    return paresis_membrane_from_field_batch(field, field_x, field_y, offs, outs, 1, n_layers, margin, dim_x, dim_y, stream);
 }
 
 // The same for several positions in one launch (blockIdx.z): the windows of different positions overlap in the field,
@@ -351,27 +325,47 @@ struct MembraneBatch {
     float* out[PARESIS_MAX_HOP_BATCH];
 };
 
+template <int ROWS>
 __global__ void __launch_bounds__(256)
 membrane_from_field_batch_kernel(const float* __restrict__ field, int field_x, int field_y, const MembraneBatch b, int n_layers, int margin,
                                  int dim_x, int dim_y) {
+    // a thread owns four columns 256 apart (every load a full 128-byte line per warp) of ROWS consecutive rows: all the
+    // loads of a layer are issued before the first add, so ROWS x 4 lines are in flight per warp and layer
     const int c0 = blockIdx.x * 1024 + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r0 = blockIdx.y * ROWS;
     const LayerOffsets& off = b.off[blockIdx.z];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[ROWS][4];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[rr][k] = 0.f;
     for (int l = 0; l < n_layers; ++l) {
-        const long long fr = off.x[l] + margin + r, fc = off.y[l] + margin + c0;
-        if (fr < 0 || fr >= field_x) continue;
-        const float* src = field + (size_t)fr * field_y;
+        const long long fc = off.y[l] + margin + c0;
+        float v[ROWS][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long f = fc + 256 * k;
-            if (c0 + 256 * k < dim_y && f >= 0 && f < field_y) acc[k] += __ldg(src + f);
+        for (int rr = 0; rr < ROWS; ++rr) {
+            const long long fr = off.x[l] + margin + r0 + rr;
+            const bool row_ok = fr >= 0 && fr < field_x && r0 + rr < dim_x;
+            const float* src = field + (size_t)(row_ok ? fr : 0) * field_y;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long f = fc + 256 * k;
+                v[rr][k] = (row_ok && c0 + 256 * k < dim_y && f >= 0 && f < field_y) ? __ldg(src + f) : 0.f;
+            }
         }
-    }
-    float* o = b.out[blockIdx.z] + (size_t)r * dim_y + c0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (c0 + 256 * k < dim_y) o[256 * k] = acc[k];
+        for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[rr][k] += v[rr][k];
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+        if (r0 + rr >= dim_x) break;
+        float* o = b.out[blockIdx.z] + (size_t)(r0 + rr) * dim_y + c0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c0 + 256 * k < dim_y) o[256 * k] = acc[rr][k];
+    }
 }
 
 extern "C" int paresis_membrane_from_field_batch(const float* field, int field_x, int field_y, const int64_t* const* offsets_host,
@@ -391,7 +385,8 @@ extern "C" int paresis_membrane_from_field_batch(const float* field, int field_x
         }
         b.out[z] = thickness_out_host[z];
     }
-    membrane_from_field_batch_kernel<<<dim3(div_up(dim_y, 1024), dim_x, n_items), 256, 0, (cudaStream_t)stream>>>(
+    constexpr int ROWS = 4;
+    membrane_from_field_batch_kernel<ROWS><<<dim3(div_up(dim_y, 1024), div_up(dim_x, ROWS), n_items), 256, 0, (cudaStream_t)stream>>>(
         field, field_x, field_y, b, n_layers, margin, dim_x, dim_y);
     PARESIS_LAUNCH_CHECK("membrane_from_field_batch_kernel");
     return PARESIS_OK;
