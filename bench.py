@@ -372,9 +372,11 @@ def run_gpu(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg = ALG_BYTES[dominant](n * n, det * det)
         traffic = None
-        traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")     # dram__bytes_{read,write}.sum of one ncu capture
-        if os.path.exists(traffic_path):
-            traffic = json.load(open(traffic_path)).get(dominant, {}).get("dram_bytes")
+        for name in ("r02_traffic.json", "r01_traffic.json"):               # dram__bytes_{read,write}.sum of one ncu --set full capture
+            traffic_path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(traffic_path):
+                traffic = json.load(open(traffic_path)).get(dominant, {}).get("dram_bytes")
+                break
         avg_ms = float(np.mean(k_ms)) if k_ms else shares[dominant]["ms_per_launch"]
         achieved = alg / (avg_ms * 1e-3) / 1e9
         line = {

@@ -5,8 +5,8 @@ set -o pipefail
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err || { echo "bench failed"; tail -5 gpurun_out/bench_default.err; exit 1; }
 tail -c 600 gpurun_out/bench_default.log; echo
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_final.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_final.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_final.csv \
+    python bench.py --steps 2 --warmup 1 --jobs-per-step 2 --no-cpu-baseline --skip-extras > gpurun_out/ncu_launches_final.log 2>&1
 python tools/one_position.py 3 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name 'regex:refract_|detect_tile|membrane_from_field' --launch-skip 4 -c 4 \
     -o gpurun_out/prof_final -f python tools/one_position.py 3 > gpurun_out/ncu_full_final.log 2>&1
