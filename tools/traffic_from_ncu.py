@@ -17,8 +17,8 @@ rows = list(csv.reader(io.StringIO(txt)))
 hdr, units, body = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
 LABELS = (("raster_spheres", ("membrane_from_field", "raster_gather", "raster_bin")),
-          ("refract_membrane_hop", ("refract_lean_kernel<1, 0")),
-          ("refract_sample_ref_hop", ("refract_lean_kernel<2, 1")),
+          ("refract_membrane_hop", ("refract_lean_kernel<1, 0",)),
+          ("refract_sample_ref_hop", ("refract_lean_kernel<2, 1",)),
           ("detect", ("detect_tile_kernel",)))
 
 
