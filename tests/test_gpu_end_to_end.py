@@ -76,7 +76,7 @@ def test_matches_reference_images(shim, golden, gold, name, model):
             if model == "RayT":
                 assert res[4].shape == (st.shape[1] + 30, st.shape[2] + 30)
                 # auxiliary output (main.py discards it): differences of fp32 thickness maps carry ~6e-8 * t/dt
-                assert rel_l2(res[4][::8, ::8], g["Dx_p0_s8"]) < 2e-4 and rel_l2(res[5][::8, ::8], g["Dy_p0_s8"]) < 2e-4
+                assert rel_l2(res[4][::8, ::8], g["Dx_p0_s8"]) < 5e-5 and rel_l2(res[5][::8, ::8], g["Dy_p0_s8"]) < 5e-5
         else:
             assert not propag.any() and not white.any()
     assert abs(e.exp_dict["meanEnergy"] / float(g["mean_energy"]) - 1) < 1e-5
