@@ -12,7 +12,7 @@
 //   * phases 2-4 (blur + bin along y, PSF along y, PSF along x) run out of shared memory with
 //     compile-time taps held in registers, several outputs per thread;
 //   * Poisson draws share one Philox block per pixel pair; draws that fail the quick PTRS test are
-//     queued and finished by dense warps.
+//     queued with their random words and finished by dense warps, step by step (poisson.cuh).
 // Instantiated per oversampling factor in detector_tile_os*.cu.
 #pragma once
 #include "detector_common.cuh"
@@ -39,12 +39,15 @@ struct DetTile {
     static constexpr int NR = UCH * OS + 2 * HS;                       // source rows a chunk reads
     static constexpr int R2W = (BWY + 3) / 4 * 4 + 4;                    // pitch of R2: 16 B rows + slack for 128-bit over-read
     static constexpr int R3W = DT_TY;
-    static constexpr int R1_FLOATS = BWX * R1W > 2 * DT_TX * DT_TY ? BWX * R1W : 2 * DT_TX * DT_TY;   // also R3 and the 2nd queue
-    static constexpr int R2_FLOATS = BWX * R2W > 2 * DT_TX * DT_TY ? BWX * R2W : 2 * DT_TX * DT_TY;   // also the Poisson queue
-    static constexpr size_t SMEM = sizeof(float) * (R1_FLOATS + R2_FLOATS) + sizeof(int) * SWX;
+    static constexpr int R1_FLOATS = BWX * R1W;                        // also R3
+    static constexpr int R2_FLOATS = BWX * R2W;
+    // Poisson queues (after phase 4 nothing else lives in R1 / R2): queue A = one 16-byte entry per pixel the quick
+    // test left open (worst case every pixel), queue B = the 8-byte entries of what step 0 rejected, behind it
+    static constexpr int QA_FLOATS = 4 * DT_TX * DT_TY, QB_CAP = 1024;
+    static constexpr int WORK_FLOATS = R1_FLOATS + R2_FLOATS > QA_FLOATS + 2 * QB_CAP ? R1_FLOATS + R2_FLOATS : QA_FLOATS + 2 * QB_CAP;
+    static constexpr size_t SMEM = sizeof(float) * WORK_FLOATS + sizeof(int) * SWX;
     static_assert(CG <= DT_THREADS, "source window too wide for one block");
     static_assert(BWX * R3W <= R1_FLOATS, "R3 must fit in R1");
-    static_assert(2 * DT_TX * DT_TY <= R1_FLOATS, "the second Poisson queue must fit in R1");
 };
 
 template <int OS, int HS, int HP>
@@ -56,7 +59,7 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
     float* R1 = dt_smem;
     float* R2 = R1 + T::R1_FLOATS;
     float* R3 = R1;
-    int* rowoff = reinterpret_cast<int*>(R2 + T::R2_FLOATS);
+    int* rowoff = reinterpret_cast<int*>(dt_smem + T::WORK_FLOATS);
     __shared__ int n_queued, n_requeued;
 
     const int tid = threadIdx.x;
@@ -88,7 +91,7 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
 #pragma unroll
     for (int t = 0; t < T::NP; ++t) P[t] = HP > 0 ? __ldg(gpsf + t) : 1.f;
 
-    if (tid == 0) n_queued = 0;
+    if (tid == 0) { n_queued = 0; n_requeued = 0; }
     for (int a = tid; a < T::SWX; a += DT_THREADS) {
         const int xp = x0 + a;
         rowoff[a] = (xp >= 0 && xp < npx) ? reflect_index(xp - pad, nx) * ny : -1;   // nx*ny < 2^30 (host check)
@@ -104,37 +107,67 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
             float4 acc[T::UCH];
 #pragma unroll
             for (int k = 0; k < T::UCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            int col[4];
-            if (!fast) {
+            if (fast && x0 >= 0 && x0 + T::SWX <= npx) {
+                // every row of the window exists and every quad is one aligned 128-bit load: no branch between the
+                // loads, so that they are all in flight together (rows past the window repeat its last row; their
+                // taps feed accumulators that are not stored)
+                const float* base = img + ya + 4 * cg;
+                constexpr int BATCH = 8;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int yp = ya + pad + 4 * cg + e;
-                    col[e] = (yp >= 0 && yp < npy) ? reflect_index(yp - pad, ny) : -1;
+                for (int r0 = 0; r0 < T::NR; r0 += BATCH) {
+                    float4 v[BATCH];
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b)
+                        if (r0 + b < T::NR) v[b] = __ldg(reinterpret_cast<const float4*>(base + rowoff[min(u_lo * OS + r0 + b, T::SWX - 1)]));
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int r = r0 + b;
+                        if (r >= T::NR) break;
+#pragma unroll
+                        for (int k = 0; k < T::UCH; ++k) {
+                            const int t = r - k * OS;   // compile-time after unrolling
+                            if (t >= 0 && t < T::TAPS) {
+                                acc[k].x = fmaf(W[t], v[b].x, acc[k].x);
+                                acc[k].y = fmaf(W[t], v[b].y, acc[k].y);
+                                acc[k].z = fmaf(W[t], v[b].z, acc[k].z);
+                                acc[k].w = fmaf(W[t], v[b].w, acc[k].w);
+                            }
+                        }
+                    }
                 }
-            }
+            } else {
+                int col[4];
+                if (!fast) {
 #pragma unroll
-            for (int r = 0; r < T::NR; ++r) {
-                const int a = u_lo * OS + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int ro = a < T::SWX ? rowoff[a] : -1;
-                if (ro >= 0) {
-                    if (fast) {
-                        v = __ldg(reinterpret_cast<const float4*>(img + ro + ya + 4 * cg));
-                    } else {
-                        if (col[0] >= 0) v.x = __ldg(img + ro + col[0]);
-                        if (col[1] >= 0) v.y = __ldg(img + ro + col[1]);
-                        if (col[2] >= 0) v.z = __ldg(img + ro + col[2]);
-                        if (col[3] >= 0) v.w = __ldg(img + ro + col[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const int yp = ya + pad + 4 * cg + e;
+                        col[e] = (yp >= 0 && yp < npy) ? reflect_index(yp - pad, ny) : -1;
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < T::UCH; ++k) {
-                    const int t = r - k * OS;   // compile-time after unrolling
-                    if (t >= 0 && t < T::TAPS) {
-                        acc[k].x = fmaf(W[t], v.x, acc[k].x);
-                        acc[k].y = fmaf(W[t], v.y, acc[k].y);
-                        acc[k].z = fmaf(W[t], v.z, acc[k].z);
-                        acc[k].w = fmaf(W[t], v.w, acc[k].w);
+                for (int r = 0; r < T::NR; ++r) {
+                    const int a = u_lo * OS + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int ro = a < T::SWX ? rowoff[a] : -1;
+                    if (ro >= 0) {
+                        if (fast) {
+                            v = __ldg(reinterpret_cast<const float4*>(img + ro + ya + 4 * cg));
+                        } else {
+                            if (col[0] >= 0) v.x = __ldg(img + ro + col[0]);
+                            if (col[1] >= 0) v.y = __ldg(img + ro + col[1]);
+                            if (col[2] >= 0) v.z = __ldg(img + ro + col[2]);
+                            if (col[3] >= 0) v.w = __ldg(img + ro + col[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < T::UCH; ++k) {
+                        const int t = r - k * OS;   // compile-time after unrolling
+                        if (t >= 0 && t < T::TAPS) {
+                            acc[k].x = fmaf(W[t], v.x, acc[k].x);
+                            acc[k].y = fmaf(W[t], v.y, acc[k].y);
+                            acc[k].z = fmaf(W[t], v.z, acc[k].z);
+                            acc[k].w = fmaf(W[t], v.w, acc[k].w);
+                        }
                     }
                 }
             }
@@ -194,13 +227,12 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
     __syncthreads();
 
     // ---- phase 4: out[a][b] = sum_e P[e] * R3[a + e][b]  (PSF along x), Poisson, store
-    int2* queue = reinterpret_cast<int2*>(R2);
+    constexpr int RB = DT_TX / (DT_THREADS / 32);     // rows per thread (4)
+    const int lane = tid & 31, warp = tid >> 5;
+    const int al = warp * RB;                         // first local row
+    float2 acc[RB];
     {
-        constexpr int RB = DT_TX / (DT_THREADS / 32);     // rows per thread (4)
-        const int lane = tid & 31, warp = tid >> 5;
-        const int al = warp * RB;                         // first local row
         const float2* src = reinterpret_cast<const float2*>(R3 + al * T::R3W + 2 * lane);
-        float2 acc[RB];
 #pragma unroll
         for (int k = 0; k < RB; ++k) acc[k] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -212,67 +244,106 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
                 if (e >= 0 && e < T::NP) { acc[k].x = fmaf(P[e], v.x, acc[k].x); acc[k].y = fmaf(P[e], v.y, acc[k].y); }
             }
         }
-        const int db = b0 + 2 * lane;
-        unsigned fail = 0u;     // bit 2k / 2k+1: left / right pixel of row k still needs poisson_slow()
+    }
+    const int db = b0 + 2 * lane;
+    if (!noise) {
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int da = a0 + al + k;
+            if (da >= det_x || db >= det_y) continue;
+            const size_t p = (size_t)da * det_y + db;
+            if (db + 1 < det_y && out_aligned && (p & 1) == 0) {
+                *reinterpret_cast<float2*>(out + p) = acc[k];
+            } else {
+                out[p] = acc[k].x;
+                if (db + 1 < det_y) out[p + 1] = acc[k].y;
+            }
+        }
+        return;
+    }
+    __syncthreads();                                  // R3 has been read: R1 / R2 become the Poisson queues
+    uint4* const qa = reinterpret_cast<uint4*>(dt_smem);
+    int2* const qb = reinterpret_cast<int2*>(dt_smem + T::QA_FLOATS);
+    {
+        // quick test of every pixel (one Philox block per aligned pixel pair); what it leaves open is queued
+        // together with its two random words, so that nothing is generated twice
 #pragma unroll
         for (int k = 0; k < RB; ++k) {
             const int da = a0 + al + k;
             if (da >= det_x || db >= det_y) continue;
             const size_t p = (size_t)da * det_y + db;
             const bool two = db + 1 < det_y;
-            const bool pair = two && out_aligned && (p & 1) == 0;
-            float x0v = acc[k].x, x1v = acc[k].y;
-            if (noise) {
-                bool ok0, ok1;
-                if (pair) {
-                    poisson_quick2(acc[k].x, acc[k].y, seed, seq, p, x0v, x1v, ok0, ok1);
-                } else {
-                    ok0 = poisson_quick(acc[k].x, seed, seq, p, x0v);
-                    ok1 = two ? poisson_quick(acc[k].y, seed, seq, p + 1, x1v) : true;
-                }
-                fail |= (ok0 ? 0u : 1u << (2 * k)) | (ok1 ? 0u : 2u << (2 * k));
-            }
+            const bool pair = two && (p & 1) == 0;
+            uint32_t r[4];
+            float x0v, x1v = 0.f;
+            bool ok0, ok1 = true;
             if (pair) {
+                Philox g = poisson_stream(seed, seq, p);
+                g.generate(r);
+                ok0 = poisson_decide(acc[k].x, r[0], r[1], x0v);
+                ok1 = poisson_decide(acc[k].y, r[2], r[3], x1v);
+            } else {
+                poisson_words(seed, seq, p, r[0], r[1]);
+                ok0 = poisson_decide(acc[k].x, r[0], r[1], x0v);
+                if (two) {
+                    poisson_words(seed, seq, p + 1, r[2], r[3]);
+                    ok1 = poisson_decide(acc[k].y, r[2], r[3], x1v);
+                }
+            }
+            if (pair && out_aligned) {
                 *reinterpret_cast<float2*>(out + p) = make_float2(x0v, x1v);
             } else {
                 out[p] = x0v;
                 if (two) out[p + 1] = x1v;
             }
-        }
-        // the rest is queued (one reservation per thread): the expensive tail runs on dense warps afterwards
-        if (fail) {
-            int slot = atomicAdd(&n_queued, __popc(fail));
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                if (fail & (1u << (2 * k))) queue[slot++] = make_int2((al + k) * DT_TY + 2 * lane, __float_as_int(acc[k].x));
-                if (fail & (2u << (2 * k))) queue[slot++] = make_int2((al + k) * DT_TY + 2 * lane + 1, __float_as_int(acc[k].y));
+            if (!(ok0 && ok1)) {
+                const int n = (ok0 ? 0 : 1) + (ok1 ? 0 : 1);
+                int slot = atomicAdd(&n_queued, n);
+                const unsigned local = (unsigned)((al + k) * DT_TY + 2 * lane);
+                if (!ok0) qa[slot++] = make_uint4(local, __float_as_uint(acc[k].x), r[0], r[1]);
+                if (!ok1) qa[slot] = make_uint4(local + 1u, __float_as_uint(acc[k].y), r[2], r[3]);
             }
         }
     }
-    if (noise) {
-        // Finish the queued draws in rounds (poisson_round: the full test of the candidate the quick test left
-        // open, then two fresh candidates per round); the few pixels still open are re-queued, so warps stay
-        // dense instead of looping on their slowest lane.
-        int2* qcur = queue;
-        int2* qnext = reinterpret_cast<int2*>(R1);     // R3 (= R1) is dead after phase 4
-        int* ncur = &n_queued;
-        int* nnext = &n_requeued;
-        for (uint32_t trial = 0; trial < 64; ++trial) {
-            __syncthreads();                           // pushes into qcur are complete
-            const int nq = *ncur;
-            if (nq == 0) break;                        // block-uniform
-            if (tid == 0) *nnext = 0;
-            __syncthreads();
-            for (int qi = tid; qi < nq; qi += DT_THREADS) {
-                const int2 e = qcur[qi];
-                const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
-                float x;
-                if (poisson_round(__int_as_float(e.y), seed, seq, p, trial, x)) out[p] = x;
-                else qnext[atomicAdd(nnext, 1)] = e;
+    __syncthreads();
+    {
+        // step 0 on dense warps: the full test of the candidate the quick test left open (or the whole draw of a
+        // small mean); what it rejects goes to queue B (or, if that is full, is finished on the spot)
+        const int nq = n_queued;
+        for (int qi = tid; qi < nq; qi += DT_THREADS) {
+            const uint4 e = qa[qi];
+            const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
+            const float lam = __uint_as_float(e.y);
+            float x;
+            if (poisson_first(lam, e.z, e.w, x)) {
+                out[p] = x;
+            } else {
+                const int slot = atomicAdd(&n_requeued, 1);
+                if (slot < T::QB_CAP) qb[slot] = make_int2((int)e.x, (int)e.y);
+                else out[p] = poisson_rest(lam, seed, seq, p, 1u);
             }
-            int2* tq = qcur; qcur = qnext; qnext = tq;
-            int* tn = ncur; ncur = nnext; nnext = tn;
         }
+    }
+    // blocks 1, 2, ... of the pixels still open, two candidates each, re-queued between blocks so that the warps stay dense
+    int2* qcur = qb;
+    int2* qnext = reinterpret_cast<int2*>(dt_smem);    // queue A is dead once step 0 is through
+    int* ncur = &n_requeued;
+    int* nnext = &n_queued;
+    for (uint32_t blk = 1; blk < 64; ++blk) {
+        __syncthreads();                               // pushes into qcur are complete, qnext has been read
+        const int nq = min(*ncur, T::QB_CAP);
+        if (nq == 0) break;                            // block-uniform
+        if (tid == 0) *nnext = 0;
+        __syncthreads();
+        for (int qi = tid; qi < nq; qi += DT_THREADS) {
+            const int2 e = qcur[qi];
+            const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
+            float x;
+            if (poisson_block(__int_as_float(e.y), seed, seq, p, blk, x)) out[p] = x;
+            else qnext[atomicAdd(nnext, 1)] = e;       // at most nq <= QB_CAP entries
+        }
+        int2* tq = qcur; qcur = qnext; qnext = tq;
+        int* tn = ncur; ncur = nnext; nnext = tn;
     }
 }
 

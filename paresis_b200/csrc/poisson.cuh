@@ -46,20 +46,33 @@ static __constant__ float LOG_FACT[16] = {0.f, 0.f, 0.69314718f, 1.79175947f, 3.
 
 // log of the Poisson pmf at k for mean lam >= 10, in fp32 without cancellation:
 //   k >= 16: Stirling,  log p = lam * g(x) - log(2 pi k)/2 - 1/(12k) + 1/(360k^3),  x = (k - lam)/lam,
-//            g(x) = x - (1+x) log(1+x)  (series for small x: the two O(lam) terms never meet)
+//            g(x) = x - (1+x) log(1+x) = sum_{n>=2} (-1)^(n+1) x^n / (n (n-1))  (the series up to x^12 for |x| < 1/4,
+//            i.e. for every candidate of a mean above ~600: the two O(lam) terms never meet, no branch, no log1p);
+//            the O(log k) terms use MUFU.LG2 / MUFU.RCP (absolute error ~1e-6 on a log-likelihood)
 //   k <  16: -lam + k log(lam) - log(k!) from the table (all terms are small there).
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float log_poisson_pmf(float k, float lam) {
     if (k < 16.f) return -lam + k * logf(lam) - LOG_FACT[(int)k];
-    const float x = (k - lam) / lam;
+    const float x = (k - lam) * rcp_approx(lam);
     float g;
-    if (fabsf(x) < 0.05f) {
-        const float x2 = x * x;
-        g = x2 * (-0.5f + x * (1.f / 6.f + x * (-1.f / 12.f + x * (0.05f + x * (-1.f / 30.f)))));
+    if (fabsf(x) < 0.25f) {
+        float h = 1.f / 132.f;                       // n = 12
+        h = fmaf(h, x, -1.f / 110.f);
+        h = fmaf(h, -x, -1.f / 90.f);
+        h = fmaf(h, -x, -1.f / 72.f);
+        h = fmaf(h, -x, -1.f / 56.f);
+        h = fmaf(h, -x, -1.f / 42.f);
+        h = fmaf(h, -x, -1.f / 30.f);
+        h = fmaf(h, -x, -1.f / 20.f);
+        h = fmaf(h, -x, -1.f / 12.f);
+        h = fmaf(h, -x, -1.f / 6.f);
+        h = fmaf(h, -x, -0.5f);
+        g = h * x * x;
     } else {
         g = x - (1.f + x) * log1pf(x);
     }
-    const float ik = 1.f / k;
-    return lam * g - 0.5f * logf(6.28318530718f * k) - ik * (1.f / 12.f - ik * ik * (1.f / 360.f));
+    const float ik = rcp_approx(k);
+    return lam * g - 0.5f * __logf(6.28318530718f * k) - ik * (1.f / 12.f - ik * ik * (1.f / 360.f));
 }
 
 // One Poisson variate with mean lam, a pure function of (seed, sequence, pixel).
@@ -145,52 +158,74 @@ __device__ __forceinline__ bool ptrs_trial(const PtrsSetup& t, float lam, float 
     return __logf(V) + log_invalpha - __logf(fmaf(t.a, rcp_fast(us * us), t.b)) <= log_poisson_pmf(k, lam);
 }
 
-// Everything the quick test leaves open, in ROUNDS so that the detector kernel can keep its warps dense:
-//   round 0 : replays the pair block of the quick test (same two words) -- lam <= 0 -> 0, lam < 10 -> inversion
-//             by sequential search, else the full PTRS test of trial 0; if that fails, rounds continue with
-//   round r : Philox block (pixel, r | 2^31) = TWO more candidates per block (words 0,1 then 2,3).
-// Returns true and the variate once the draw is decided.  A draw is still a pure function of
-// (seed, sequence, pixel): poisson_draw() below walks the same rounds.
-static __device__ __noinline__ bool poisson_round(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t round,
-                                                  float& result) {
+// Everything the quick test leaves open, in STEPS that a kernel can run on dense warps:
+//   step 0 (poisson_first) : the two words of the pair block that the quick test saw -- lam <= 0 -> 0, lam < 10 ->
+//             inversion by sequential search, else the full PTRS test of candidate 0;
+//   step n >= 1 (poisson_block): Philox block (pixel, n | 2^31) = TWO more candidates (words 0,1 then 2,3).
+// Each returns true and the variate once the draw is decided.  A draw stays a pure function of (seed, sequence,
+// pixel): poisson_round() / poisson_draw() below walk the same steps.
+__device__ __forceinline__ bool poisson_first(float lam, uint32_t ra, uint32_t rb, float& result) {
     if (!(lam > 0.f)) { result = 0.f; return true; }
-    uint32_t r[4];
-    if (round == 0) {
-        Philox g = poisson_stream(seed, seq, pixel);
-        g.generate(r);
-        const bool hi = pixel & 1;
-        const uint32_t ra = hi ? r[2] : r[0], rb = hi ? r[3] : r[1];
-        if (lam < 10.f) {
-            const float u = (float)u01d(ra, rb);
-            float p = expf(-lam), F = p;
-            int x = 0;
-            while (u > F && x < 200) {
-                ++x;
-                p *= lam / (float)x;
-                F += p;
-            }
-            result = (float)x;
-            return true;
+    if (lam < 10.f) {
+        const float u = (float)u01d(ra, rb);
+        float p = expf(-lam), F = p;
+        int x = 0;
+        while (u > F && x < 200) {
+            ++x;
+            p *= lam / (float)x;
+            F += p;
         }
-        const PtrsSetup t(lam);
-        const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
-        if (ptrs_trial(t, lam, log_invalpha, ra, rb, result)) return true;
-        round = 1;      // ~82 % of the queued candidates are rejected: go on with this pixel's own block right away
-    } else {
-        ++round;        // caller's round r >= 1 is block r + 1 (block 1 was consumed inside round 0)
+        result = (float)x;
+        return true;
     }
+    const PtrsSetup t(lam);
+    const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
+    return ptrs_trial(t, lam, log_invalpha, ra, rb, result);
+}
+
+__device__ __forceinline__ bool poisson_block(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t block, float& result) {
     const PtrsSetup t(lam);
     const float log_invalpha = __logf(1.1239f + 1.1328f * rcp_fast(t.b - 3.4f));
     Philox g;
     g.c[0] = (uint32_t)pixel;
-    g.c[1] = round | 0x80000000u;
+    g.c[1] = block | 0x80000000u;
     g.c[2] = (uint32_t)seq;
     g.c[3] = (uint32_t)(seq >> 32) ^ (uint32_t)(pixel >> 32);
     g.k[0] = (uint32_t)seed;
     g.k[1] = (uint32_t)(seed >> 32);
+    uint32_t r[4];
     g.generate(r);
     if (ptrs_trial(t, lam, log_invalpha, r[0], r[1], result)) return true;
     return ptrs_trial(t, lam, log_invalpha, r[2], r[3], result);
+}
+
+// The two random words of `pixel` in its pair block (what poisson_quick / poisson_quick2 consumed).
+__device__ __forceinline__ void poisson_words(uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t& ra, uint32_t& rb) {
+    Philox g = poisson_stream(seed, seq, pixel);
+    uint32_t r[4];
+    g.generate(r);
+    const bool hi = pixel & 1;
+    ra = hi ? r[2] : r[0];
+    rb = hi ? r[3] : r[1];
+}
+
+// Round 0 = step 0 and, if that rejects (~55 % of what reaches it), block 1 right away; round r >= 1 = block r + 1.
+static __device__ __noinline__ bool poisson_round(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t round,
+                                                  float& result) {
+    if (round == 0) {
+        uint32_t ra, rb;
+        poisson_words(seed, seq, pixel, ra, rb);
+        if (poisson_first(lam, ra, rb, result)) return true;
+    }
+    return poisson_block(lam, seed, seq, pixel, round + 1, result);
+}
+
+// Blocks first, first + 1, ... until the draw is decided (after step 0 rejected).
+static __device__ __noinline__ float poisson_rest(float lam, uint64_t seed, uint64_t seq, uint64_t pixel, uint32_t first) {
+    float x;
+    for (uint32_t blk = first; blk < first + 32; ++blk)
+        if (poisson_block(lam, seed, seq, pixel, blk, x)) return x;
+    return floorf(lam + 0.5f);  // unreachable in practice (two candidates per block, acceptance > 0.88 each)
 }
 
 // The complete draw.

@@ -93,10 +93,12 @@ __device__ __forceinline__ void flush_rows_fast(const unsigned* tile, float* out
 #endif
 constexpr unsigned MISS_REF = 0x40000000u, MISS_TWIN = 0x80000000u;
 
-template <int NM, bool DUAL, bool HAS_I, int TR, int MQ>
+template <int NM, bool DUAL, bool HAS_I, int TR, int MQ, bool ZB>
 __global__ void __launch_bounds__(TILE_COLS, LEAN_MIN_BLOCKS(DUAL, NM))
 refract_lean_kernel(const LeanArgs a) {
-    const LeanItem& it = a.z[blockIdx.z];          // this block's membrane position
+    // this block's membrane position; a single-position launch (ZB = false) addresses its pointers as plain kernel
+    // parameters instead of through a register-indexed constant load per use
+    const LeanItem& it = a.z[ZB ? blockIdx.z : 0];
     constexpr int H = 4;
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H, NT = DUAL ? 2 : 1;
     static_assert(((1ull << 32) / (TR * TILE_COLS)) >= (2ull << FIX_BITS), "rays up to 2 x intensity_scale must fit the fixed-point tile");
@@ -374,9 +376,10 @@ static int launch_refract_lean(const LeanArgs& a_in, int n_batch, cudaStream_t s
     PARESIS_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 32) dev = 0;
     if (!slots_of[dev]) {
-        PARESIS_CUDA(cudaFuncSetAttribute(refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PARESIS_CUDA(cudaFuncSetAttribute(refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PARESIS_CUDA(cudaFuncSetAttribute(refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
-        PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ>, TILE_COLS, smem));
+        PARESIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, false>, TILE_COLS, smem));
         PARESIS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         slots_of[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
@@ -384,7 +387,8 @@ static int launch_refract_lean(const LeanArgs& a_in, int n_batch, cudaStream_t s
     const int strips = div_up(a.f.ny, TILE_COLS);
     a.rows = pick_tile_rows(a.f.nx, strips * n_batch, slots_of[dev], TR);
     dim3 grid(strips, div_up(a.f.nx, a.rows), n_batch);
-    refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ><<<grid, TILE_COLS, smem, s>>>(a);
+    if (n_batch > 1) refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, true><<<grid, TILE_COLS, smem, s>>>(a);
+    else refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, false><<<grid, TILE_COLS, smem, s>>>(a);
     PARESIS_LAUNCH_CHECK("refract_lean_kernel");
     return PARESIS_OK;
 }
