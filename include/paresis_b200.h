@@ -296,10 +296,13 @@ int paresis_transmit_wave(const paresis_c32* wave_in, float amplitude_uniform,
                           paresis_c32* wave_out, size_t n, paresis_stream stream);
 
 typedef struct paresis_fresnel_plan paresis_fresnel_plan;
+typedef struct paresis_fresnel_kernel paresis_fresnel_kernel;
 
-/* Experiment.wavePropagation (Experiment.py:219-252): reflect-pad by `margin`, FFT,
- * multiply by the separable transfer function, inverse FFT, crop.  The plan owns the cuFFT
- * C2C plan of size (nx+2m) x (ny+2m) and the padded work buffer. */
+/* Experiment.wavePropagation (Experiment.py:219-252): reflect-pad by `margin` (<= 16), FFT at the padded size P = n + 2m,
+ * multiply by the separable transfer function, inverse FFT, crop.  Evaluated as what it is -- a circular convolution of
+ * period P along each axis, cropped to the n core samples -- with batched 1-D transforms of a convenient length
+ * M >= 2n - 1 (a power of two at the benchmark grids, where P = 2 x prime) plus the 2m reflect-margin terms in closed
+ * form (csrc/fresnel.cu).  The plan owns the cuFFT line plans, an n x M work buffer and an n x n intermediate. */
 int paresis_fresnel_plan_create(int nx, int ny, int margin, paresis_fresnel_plan** plan);
 int paresis_fresnel_plan_destroy(paresis_fresnel_plan* plan);
 size_t paresis_fresnel_plan_bytes(const paresis_fresnel_plan* plan);
@@ -309,15 +312,25 @@ size_t paresis_fresnel_plan_bytes(const paresis_fresnel_plan* plan);
  * (Experiment.py:243-250; the frequency step uses the UNPADDED size, :246-247).
  * `phase` multiplies the result (the global exp(ikz/M) of :250, or 1).
  * If intensity_acc != NULL the kernel adds |wave|^2 into it (Experiment.py:351-358) and
- * wave_out may be NULL. */
+ * wave_out may be NULL; wave_out may be wave_in. */
 int paresis_fresnel_propagate(paresis_fresnel_plan* plan, const paresis_c32* wave_in,
                               const paresis_c32* hx, const paresis_c32* hy, paresis_c32 phase,
                               paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);
 
-/* Several propagations of the SAME field over different distances (Experiment.py:340-341 and :349 both start from the
- * wave behind the membrane): paresis_fresnel_spectrum keeps fft2(np.pad(wave, margin, 'reflect')) inside the plan
- * (a second padded buffer, allocated on first use), paresis_fresnel_from_spectrum applies one transfer function to it,
- * transforms back, crops and delivers like paresis_fresnel_propagate.  One forward transform saved per extra distance. */
+/* The same in two steps, for a transfer function that is used more than once (every membrane position of a scan uses
+ * the same distances and energies): paresis_fresnel_kernel_create turns (hx, hy) into the convolution kernels of both
+ * axes (fp64 on the device, a few small launches on `stream`), paresis_fresnel_convolve propagates with them. */
+int paresis_fresnel_kernel_create(paresis_fresnel_plan* plan, const paresis_c32* hx, const paresis_c32* hy, paresis_stream stream,
+                                  paresis_fresnel_kernel** kernel);
+int paresis_fresnel_kernel_destroy(paresis_fresnel_kernel* kernel);
+int paresis_fresnel_convolve(paresis_fresnel_plan* plan, const paresis_c32* wave_in, const paresis_fresnel_kernel* kernel,
+                             paresis_c32 phase, paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);
+
+/* The literal chain, kept as a cross-check of the above and for callers that want the padded spectrum: several
+ * propagations of the SAME field over different distances (Experiment.py:340-341 and :349 both start from the wave
+ * behind the membrane).  paresis_fresnel_spectrum keeps fft2(np.pad(wave, margin, 'reflect')) inside the plan (cuFFT 2-D
+ * plan of size P x P and two padded buffers, allocated on first use), paresis_fresnel_from_spectrum applies one transfer
+ * function to it, transforms back, crops and delivers like paresis_fresnel_propagate. */
 int paresis_fresnel_spectrum(paresis_fresnel_plan* plan, const paresis_c32* wave_in, paresis_stream stream);
 int paresis_fresnel_from_spectrum(paresis_fresnel_plan* plan, const paresis_c32* hx, const paresis_c32* hy, paresis_c32 phase,
                                   paresis_c32* wave_out, float* intensity_acc, paresis_stream stream);

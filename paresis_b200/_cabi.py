@@ -24,7 +24,8 @@ REFRACTION_MARGIN_V1 = 10  # refractionFileNumba.py:36
 EXPORTS = (
     "paresis_version", "paresis_last_error", "paresis_set_tuning", "paresis_trim", "paresis_splat", "paresis_refract_phi", "paresis_refract_layers",
     "paresis_transmit_rt", "paresis_transmit_wave", "paresis_fresnel_plan_create", "paresis_fresnel_plan_destroy",
-    "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_fresnel_spectrum", "paresis_fresnel_from_spectrum", "paresis_detect_work_floats", "paresis_detect",
+    "paresis_fresnel_plan_bytes", "paresis_fresnel_propagate", "paresis_fresnel_kernel_create", "paresis_fresnel_kernel_destroy",
+    "paresis_fresnel_convolve", "paresis_fresnel_spectrum", "paresis_fresnel_from_spectrum", "paresis_detect_work_floats", "paresis_detect",
     "paresis_detect_counts", "paresis_detect_counts_multi",
     "paresis_poisson", "paresis_bin_sum", "paresis_raster_work_bytes", "paresis_raster_spheres", "paresis_sphere_map", "paresis_cylinder_map",
     "paresis_fill", "paresis_axpy", "paresis_mean", "paresis_sum_scaled", "paresis_rt_run", "paresis_rt_run_positions",
@@ -128,6 +129,9 @@ def _load():
         "paresis_fresnel_plan_create": [ci, ci, ci, ctypes.POINTER(vp)],
         "paresis_fresnel_plan_destroy": [vp],
         "paresis_fresnel_propagate": [vp, vp, vp, vp, C32, vp, vp, vp],
+        "paresis_fresnel_kernel_create": [vp, vp, vp, vp, ctypes.POINTER(vp)],
+        "paresis_fresnel_kernel_destroy": [vp],
+        "paresis_fresnel_convolve": [vp, vp, vp, C32, vp, vp, vp],
         "paresis_fresnel_spectrum": [vp, vp, vp],
         "paresis_fresnel_from_spectrum": [vp, vp, vp, C32, vp, vp, vp],
         "paresis_detect": [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp, vp, vp],
@@ -419,7 +423,17 @@ class FresnelPlan:
                                              _ptr(hy, torch.complex64), ph, _ptr(wave_out, torch.complex64),
                                              _ptr(intensity_acc, torch.float32), _stream()),
                "paresis_fresnel_propagate")
-        _count(5)
+        _count(16)
+
+    def kernel(self, hx, hy):
+        """The convolution kernels of one transfer function (both axes), for convolve()."""
+        return FresnelKernel(self, hx, hy)
+
+    def convolve(self, wave_in, kernel, phase=1.0 + 0.0j, wave_out=None, intensity_acc=None):
+        ph = C32(float(np.real(phase)), float(np.imag(phase)))
+        _check(lib.paresis_fresnel_convolve(self._h, _ptr(wave_in, torch.complex64), kernel._h, ph, _ptr(wave_out, torch.complex64),
+                                            _ptr(intensity_acc, torch.float32), _stream()), "paresis_fresnel_convolve")
+        _count(6)
 
     def spectrum(self, wave_in):
         """fft2(pad(wave_in)) kept inside the plan for from_spectrum()."""
@@ -436,6 +450,26 @@ class FresnelPlan:
     def close(self):
         if self._h:
             lib.paresis_fresnel_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FresnelKernel:
+    def __init__(self, plan, hx, hy):
+        h = ctypes.c_void_p()
+        _check(lib.paresis_fresnel_kernel_create(plan._h, _ptr(hx, torch.complex64), _ptr(hy, torch.complex64), _stream(),
+                                                 ctypes.byref(h)), "paresis_fresnel_kernel_create")
+        self._h = h
+        _count(10)
+
+    def close(self):
+        if self._h:
+            lib.paresis_fresnel_kernel_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -305,12 +305,15 @@ refract_lean_kernel(const LeanArgs a) {
                         gy = rt - lf;
                         gx = dn - up;
                     } else {
-                        // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54)
+                        // np.gradient(edge_order=2) numerators times 2h (refractionFileNumba2.py:54).  The third sample
+                        // of a one-sided difference is two lanes away in this warp's own row (a load here would sit at L2
+                        // latency on every row of every border warp, and the block waits for its slowest warp)
                         const float* r = t + (size_t)i * f.ny;
-                        if (jc == 0) gy = -3.f * mid + 4.f * rt - __ldg(r + 2);
-                        else if (jc == f.ny - 1) gy = 3.f * mid - 4.f * lf + __ldg(r + f.ny - 3);
+                        const float two_up = __shfl_sync(FULL_MASK, mid, 2), two_down = __shfl_sync(FULL_MASK, mid, (lane + 30) & 31);
+                        if (jc == 0) gy = -3.f * mid + 4.f * rt - (f.ny > 2 ? two_up : __ldg(r + 2));
+                        else if (jc == f.ny - 1) gy = 3.f * mid - 4.f * lf + (lane >= 2 && live ? two_down : __ldg(r + f.ny - 3));
                         else gy = rt - lf;
-                        if (i == 0) gx = -3.f * mid + 4.f * dn - __ldg(t + (size_t)2 * f.ny + jc);
+                        if (i == 0) gx = -3.f * mid + 4.f * dn - (f.nx > 2 ? row[knew][m] : __ldg(t + (size_t)2 * f.ny + jc));
                         else if (i == f.nx - 1) gx = 3.f * mid - 4.f * up + __ldg(t + (size_t)(f.nx - 3) * f.ny + jc);
                         else gx = dn - up;
                     }

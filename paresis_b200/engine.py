@@ -457,16 +457,18 @@ class ImageFormation:
         if key not in self._vectors:
             hx, hy, phase = hm.fresnel_vectors(self.nx, self.ny, 15, scene.study_dims, scene.study_pixel_um,
                                                distance, energy, magnification)
-            self._vectors[key] = (torch.as_tensor(hx, device=self.device), torch.as_tensor(hy, device=self.device), phase)
+            hx, hy = torch.as_tensor(hx, device=self.device), torch.as_tensor(hy, device=self.device)
+            # the convolution kernels of this transfer function, prepared once for every position of the scan
+            self._vectors[key] = (self._plan.kernel(hx, hy), phase)
         return self._vectors[key]
 
     @_on_own_device
     def propagate(self, scene, wave_in, distance, energy, magnification, wave_out=None, intensity_acc=None):
         """Experiment.wavePropagation (Experiment.py:219-252) on device fields."""
         self._fresnel_setup()
-        hx, hy, phase = self._transfer(scene, distance, energy, magnification)
+        kern, phase = self._transfer(scene, distance, energy, magnification)
         # |.|^2 ignores the global phase; a returned field carries it (formed in fp64 on the host)
-        self._plan.propagate(wave_in, hx, hy, phase if wave_out is not None else 1.0, wave_out, intensity_acc)
+        self._plan.convolve(wave_in, kern, phase if wave_out is not None else 1.0, wave_out, intensity_acc)
 
     @_on_own_device
     def compute_fresnel(self, scene, point_num, sequence_base=0):
@@ -491,14 +493,10 @@ class ImageFormation:
             # after the membrane (:338); uniform layers: attenuation folded in, constant phase dropped
             abi.transmit_wave(None, amp * np.exp(-k * mem_ub), [t for t, _, _ in mem_maps],
                               [k * b for _, _, b in mem_maps], [k * d for _, d, _ in mem_maps], w_a)
-            # Both beams start from the wave behind the membrane: its reflect-pad + forward FFT is done once.
             # reference beam: membrane -> detector in one hop (:349, :354)
-            self._plan.spectrum(w_a)
-            hx, hy, phase = self._transfer(s, s.d3 + s.d2, energy, s.magnification)
-            self._plan.from_spectrum(hx, hy, 1.0, None, self.acc["reference"])
+            self.propagate(s, w_a, s.d3 + s.d2, energy, s.magnification, intensity_acc=self.acc["reference"])
             # sample beam: membrane -> object (:340-341), through the sample (:344), -> detector (:348)
-            hx, hy, phase = self._transfer(s, s.d2, energy, mag_mem_obj)
-            self._plan.from_spectrum(hx, hy, phase, w_b, None)
+            self.propagate(s, w_a, s.d2, energy, mag_mem_obj, wave_out=w_b)
             abi.transmit_wave(w_b, 0.0, [t for t, _, _ in smp_maps], [k * b for _, _, b in smp_maps],
                               [k * d for _, d, _ in smp_maps], w_b)
             self.propagate(s, w_b, s.d3, energy, s.magnification, intensity_acc=self.acc["sample"])

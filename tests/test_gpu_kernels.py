@@ -291,6 +291,46 @@ def test_fresnel_propagation(abi, golden):
     plan.close()
 
 
+@pytest.mark.parametrize("shape,margin", [((96, 128), 15), ((70, 111), 15), ((129, 64), 7), ((50, 50), 0), ((300, 260), 16)])
+def test_fresnel_separable_path_is_the_padded_transform(abi, shape, margin):
+    """The production propagator (per-axis circular convolution of period n + 2m through power-of-two line transforms plus the
+    reflect-margin terms, csrc/fresnel.cu) against numpy's literal pad -> fft2 -> transfer -> ifft2 -> crop (Experiment.py:236-251)
+    in fp64, and against the library's own literal chain (paresis_fresnel_spectrum / _from_spectrum)."""
+    from paresis_b200 import hostmath as hm
+    nx, ny = shape
+    rng = np.random.default_rng(nx * 1000 + ny)
+    wave = (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(np.complex64)
+    plan = abi.FresnelPlan(nx, ny, margin)
+    w_in = dev(wave, torch.complex64)
+    for z, E, M, pix in ((0.7, 22.0, 1.3, 0.9), (3.0, 17.0, 2.0, 2.5)):
+        hx, hy, phase = hm.fresnel_vectors(nx, ny, margin, (nx, ny), pix, z, E, M)
+        padded = np.pad(wave.astype(np.complex128), margin, mode="reflect") if margin else wave.astype(np.complex128)
+        h2 = hx.astype(np.complex128)[:, None] * hy.astype(np.complex128)[None, :]
+        full = np.fft.ifft2(np.fft.fft2(padded) * h2) * (padded.shape[0] * padded.shape[1])     # the vectors carry the 1/(Px Py)
+        want = full[margin:margin + nx, margin:margin + ny]
+        hx_d, hy_d = dev(hx, torch.complex64), dev(hy, torch.complex64)
+        got = torch.empty(shape, device="cuda", dtype=torch.complex64)
+        acc = torch.full(shape, 2.0, device="cuda")
+        kern = plan.kernel(hx_d, hy_d)
+        plan.convolve(w_in, kern, 1.0, got, acc)
+        def dist(a, b):      # complex-aware (conftest.rel_l2 is for real images)
+            return float(np.linalg.norm(a.astype(np.complex128) - b) / np.linalg.norm(b))
+        assert dist(got.cpu().numpy(), want) < 2e-6
+        assert rel_l2(acc.cpu().numpy() - 2.0, np.abs(want) ** 2) < 1e-5
+        again = torch.empty_like(got)
+        plan.propagate(w_in, hx_d, hy_d, 1.0, again, None)
+        assert torch.equal(again, got)
+        inplace = w_in.clone()
+        plan.convolve(inplace, kern, 1.0, inplace, None)
+        assert torch.equal(inplace, got)
+        lit = torch.empty_like(got)
+        plan.spectrum(w_in)
+        plan.from_spectrum(hx_d, hy_d, 1.0, lit, None)
+        assert dist(lit.cpu().numpy(), want) < 2e-6
+        kern.close()
+    plan.close()
+
+
 def test_detection(abi, golden):
     from paresis_b200 import hostmath as hm
     g = golden("detector")
