@@ -18,12 +18,16 @@
 #include <cufft.h>
 
 #include <algorithm>
+#include <cmath>
+#include <vector>
 
 #include "common.cuh"
+#include "fresnel_lines.cuh"
 
 struct paresis_fresnel_kernel {
     float2* g[2];     // [0]: along x (lines of the second pass, M_x values), [1]: along y
     float2* c[2];     // the spatial kernels, P_x / P_y values
+    float2* g_dr[2];  // g in the digit-reversed, pair-major order of the in-shared-memory transform (axes that use it)
 };
 
 struct paresis_fresnel_plan {
@@ -36,6 +40,9 @@ struct paresis_fresnel_plan {
     float2* work;                             // max(nx * M_y, ny * M_x)
     float2* mid;                              // ny x nx: the wave after the first pass, transposed
     double2* zbuf;                            // max(P, M) of both axes
+    bool fused[2];                            // M is a power of two in [512, 16384]: line_convolve_kernel instead of cuFFT
+    int log_m[2];
+    float2* tw[2];                            // per-pass twiddle tables of line_convolve_kernel
     paresis_fresnel_kernel own;               // kernels of paresis_fresnel_propagate(hx, hy)
     size_t line_bytes;
     // literal path (spectrum / from_spectrum), created on first use
@@ -123,21 +130,25 @@ mul_lines_kernel(float2* __restrict__ work, const float2* __restrict__ G, int M)
 }
 
 // out[s][l] = (work[l][s] + margin terms) * phase for s < n, transposed through shared memory; the last pass can add
-// |.|^2 into acc instead of (or besides) storing the field.  32 lines x 32 samples per block of 32 x 8 threads.
+// |.|^2 into acc instead of (or besides) storing the field.  32 lines x 32 samples per block of 32 x 8 threads; a thread
+// owns four lines of one sample.  MARGIN > 0: compile-time margin (the loop over the 2m terms unrolls, every shared-memory
+// offset is an immediate); MARGIN = 0: run-time margin m.
 constexpr int POST_T = 32, POST_MAXM = 16;
+template <int MARGIN>
 __global__ void __launch_bounds__(256)
-post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in, const float2* __restrict__ c, int lines, int n, int m,
-                  int M, float2 phase, float2* __restrict__ out, float* __restrict__ acc) {
+post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in, const float2* __restrict__ c, int lines, int n, int m_rt,
+                  int pitch, float2 phase, float2* __restrict__ out, float* __restrict__ acc) {
     __shared__ float2 tile[POST_T][POST_T + 1];
-    __shared__ float2 edge[POST_T][2 * POST_MAXM];
+    __shared__ float2 edge[2 * POST_MAXM][POST_T + 1];      // [term][line]: the four lines of a thread are 8 apart
     __shared__ float2 cwin[POST_T + 2 * POST_MAXM];
+    const int m = MARGIN > 0 ? MARGIN : m_rt;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POST_T + tx;
     const int s0 = blockIdx.x * POST_T, l0 = blockIdx.y * POST_T;
     // the 2m samples of each line that the reflect margins repeat, and the kernel values this tile meets
     for (int k = tid; k < POST_T * 2 * m; k += 256) {
         const int l = k / (2 * m), j = k - l * 2 * m;
         const int src = j < m ? j + 1 : n - 2 - (j - m);
-        edge[l][j] = l0 + l < lines ? in[(size_t)(l0 + l) * n + src] : make_float2(0.f, 0.f);
+        edge[j][l] = l0 + l < lines ? in[(size_t)(l0 + l) * n + src] : make_float2(0.f, 0.f);
     }
     for (int k = tid; k < POST_T + 2 * m; k += 256) cwin[k] = c[min(s0 + 1 + k, n + 2 * m - 1)];
     __syncthreads();
@@ -146,13 +157,16 @@ post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in
 #pragma unroll
     for (int i = 0; i < POST_T / 8; ++i) {
         const int l = l0 + ty + 8 * i;
-        v[i] = (s < n && l < lines) ? work[(size_t)l * M + s] : make_float2(0.f, 0.f);
+        v[i] = (s < n && l < lines) ? work[(size_t)l * pitch + s] : make_float2(0.f, 0.f);
     }
-    for (int j = 0; j < 2 * m; ++j) {
+    // term j < m: core[j + 1] c[s + j + 1];  term j >= m: core[n - 2 - (j - m)] c[s + 3m - j]
+#pragma unroll
+    for (int j = 0; j < (MARGIN > 0 ? 2 * MARGIN : 2 * POST_MAXM); ++j) {
+        if (MARGIN == 0 && j >= 2 * m) break;
         const float2 cv = cwin[j < m ? tx + j : tx + 3 * m - j - 1];
 #pragma unroll
         for (int i = 0; i < POST_T / 8; ++i) {
-            const float2 e = edge[ty + 8 * i][j];
+            const float2 e = edge[j][ty + 8 * i];
             v[i].x = fmaf(e.x, cv.x, fmaf(-e.y, cv.y, v[i].x));
             v[i].y = fmaf(e.x, cv.y, fmaf(e.y, cv.x, v[i].y));
         }
@@ -189,18 +203,47 @@ __global__ void arrange_kernel(const double2* __restrict__ cz, int n, int P, int
         g[k] = v;
     }
 }
-__global__ void narrow_kernel(const double2* __restrict__ g, int M, float2* __restrict__ G) {
+__global__ void narrow_kernel(const double2* __restrict__ g, int M, float2* __restrict__ G, float2* __restrict__ G_dr, int log_m) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < M) G[k] = make_float2((float)(g[k].x / M), (float)(g[k].y / M));
+    if (k >= M) return;
+    G[k] = make_float2((float)(g[k].x / M), (float)(g[k].y / M));
+    if (G_dr) {
+        // position k of the digit-reversed spectrum holds frequency fl_frequency_of(k); the middle pass reads group
+        // b = k / R pair by pair, pair h of all groups together
+        const int fr = fl_frequency_of(k, log_m), lr = fl_log_mid(log_m), R = 1 << lr, groups = M >> lr;
+        const int b = k >> lr, within = k & (R - 1);
+        G_dr[((within >> 1) * groups + b) * 2 + (within & 1)] = make_float2((float)(g[fr].x / M), (float)(g[fr].y / M));
+    }
 }
 
-// smallest even M >= 2n - 1 whose prime factors are 2, 3, 5, 7 (cuFFT's fast radices)
+// Convolution length M >= 2n - 1: the next power of two when that is in the range of the in-shared-memory transform and
+// not much longer than the smallest even length with prime factors 2, 3, 5, 7 (cuFFT's fast radices), else the latter.
 static int conv_length(int n) {
-    for (int M = (2 * n - 1 + 1) & ~1;; M += 2) {
-        int r = M;
+    int smooth = (2 * n - 1 + 1) & ~1;
+    for (;; smooth += 2) {
+        int r = smooth;
         for (int q : {2, 3, 5, 7}) while (r % q == 0) r /= q;
-        if (r == 1) return M;
+        if (r == 1) break;
     }
+    int pow2 = 512;
+    while (pow2 < 2 * n - 1) pow2 *= 2;
+    return (pow2 <= 16384 && 2 * pow2 <= 3 * smooth) ? pow2 : smooth;
+}
+
+template <int LOG_M>
+static int launch_line_convolve(const float2* in, int lines, int n, const float2* tw, const float2* g_dr, float2* out, cudaStream_t s) {
+    static bool configured[32] = {false};     // per device
+    int dev = 0;
+    PARESIS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 32) dev = 0;
+    const size_t smem = fl_smem_bytes(LOG_M);
+    if (!configured[dev]) {
+        PARESIS_CUDA(cudaFuncSetAttribute(line_convolve_kernel<LOG_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = true;
+    }
+    line_convolve_kernel<LOG_M><<<lines, fl_threads(LOG_M), smem, s>>>(in, n, tw, reinterpret_cast<const float4*>(g_dr), out);
+    PARESIS_LAUNCH_CHECK("line_convolve_kernel");
+    return PARESIS_OK;
 }
 
 static int fft_error(cufftResult r, const char* what) {
@@ -209,15 +252,21 @@ static int fft_error(cufftResult r, const char* what) {
 }
 
 static int kernel_alloc(const paresis_fresnel_plan* p, paresis_fresnel_kernel* k) {
-    for (int ax = 0; ax < 2; ++ax) { k->g[ax] = nullptr; k->c[ax] = nullptr; }
+    for (int ax = 0; ax < 2; ++ax) { k->g[ax] = nullptr; k->c[ax] = nullptr; k->g_dr[ax] = nullptr; }
     for (int ax = 0; ax < 2; ++ax) {
         PARESIS_CUDA(cudaMalloc(&k->g[ax], sizeof(float2) * p->fft_len[ax]));
         PARESIS_CUDA(cudaMalloc(&k->c[ax], sizeof(float2) * p->period[ax]));
+        if (p->fused[ax]) PARESIS_CUDA(cudaMalloc(&k->g_dr[ax], sizeof(float2) * p->fft_len[ax]));
     }
     return PARESIS_OK;
 }
 static void kernel_free(paresis_fresnel_kernel* k) {
-    for (int ax = 0; ax < 2; ++ax) { if (k->g[ax]) cudaFree(k->g[ax]); if (k->c[ax]) cudaFree(k->c[ax]); k->g[ax] = k->c[ax] = nullptr; }
+    for (int ax = 0; ax < 2; ++ax) {
+        if (k->g[ax]) cudaFree(k->g[ax]);
+        if (k->c[ax]) cudaFree(k->c[ax]);
+        if (k->g_dr[ax]) cudaFree(k->g_dr[ax]);
+        k->g[ax] = k->c[ax] = k->g_dr[ax] = nullptr;
+    }
 }
 
 static int kernel_fill(paresis_fresnel_plan* p, const float2* hx, const float2* hy, paresis_fresnel_kernel* k, cudaStream_t s) {
@@ -237,9 +286,17 @@ static int kernel_fill(paresis_fresnel_plan* p, const float2* hx, const float2* 
         r = cufftSetStream(p->zm[ax], s);
         if (r == CUFFT_SUCCESS) r = cufftExecZ2Z(p->zm[ax], (cufftDoubleComplex*)gz, (cufftDoubleComplex*)gz, CUFFT_FORWARD);
         if (r != CUFFT_SUCCESS) return fft_error(r, "cufftExecZ2Z (kernel, convolution length)");
-        narrow_kernel<<<(M + 255) / 256, 256, 0, s>>>(gz, M, k->g[ax]);
+        narrow_kernel<<<(M + 255) / 256, 256, 0, s>>>(gz, M, k->g[ax], p->fused[ax] ? k->g_dr[ax] : nullptr, p->log_m[ax]);
         PARESIS_LAUNCH_CHECK("narrow_kernel");
     }
+    return PARESIS_OK;
+}
+
+static int launch_post(dim3 grid, const float2* work, const float2* in, const float2* c, int lines, int n, int m, int pitch, float2 phase,
+                       float2* out, float* acc, cudaStream_t s) {
+    if (m == 15) post_lines_kernel<15><<<grid, dim3(POST_T, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
+    else post_lines_kernel<0><<<grid, dim3(POST_T, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
+    PARESIS_LAUNCH_CHECK("post_lines_kernel");
     return PARESIS_OK;
 }
 
@@ -247,6 +304,20 @@ static int kernel_fill(paresis_fresnel_plan* p, const float2* hx, const float2* 
 static int convolve_axis(paresis_fresnel_plan* p, int ax, const float2* in, int lines, const paresis_fresnel_kernel* k, float2 phase,
                          float2* out, float* acc, cudaStream_t s) {
     const int n = p->len[ax], M = p->fft_len[ax], m = p->margin;
+    const dim3 gt((n + POST_T - 1) / POST_T, (lines + POST_T - 1) / POST_T);
+    if (p->fused[ax]) {
+        int rc;
+        switch (p->log_m[ax]) {
+            case 9: rc = launch_line_convolve<9>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+            case 10: rc = launch_line_convolve<10>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+            case 11: rc = launch_line_convolve<11>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+            case 12: rc = launch_line_convolve<12>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+            case 13: rc = launch_line_convolve<13>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+            default: rc = launch_line_convolve<14>(in, lines, n, p->tw[ax], k->g_dr[ax], p->work, s); break;
+        }
+        if (rc != PARESIS_OK) return rc;
+        return launch_post(gt, p->work, in, k->c[ax], lines, n, m, n, phase, out, acc, s);
+    }
     const dim3 gl((M / 2 + 255) / 256, lines);
     pad_lines_kernel<<<gl, 256, 0, s>>>(in, lines, n, M, p->work);
     PARESIS_LAUNCH_CHECK("pad_lines_kernel");
@@ -257,10 +328,7 @@ static int convolve_axis(paresis_fresnel_plan* p, int ax, const float2* in, int 
     PARESIS_LAUNCH_CHECK("mul_lines_kernel");
     r = cufftExecC2C(p->lines[ax], p->work, p->work, CUFFT_INVERSE);
     if (r != CUFFT_SUCCESS) return fft_error(r, "cufftExecC2C inverse (lines)");
-    const dim3 gt((n + POST_T - 1) / POST_T, (lines + POST_T - 1) / POST_T);
-    post_lines_kernel<<<gt, dim3(POST_T, 8), 0, s>>>(p->work, in, k->c[ax], lines, n, m, M, phase, out, acc);
-    PARESIS_LAUNCH_CHECK("post_lines_kernel");
-    return PARESIS_OK;
+    return launch_post(gt, p->work, in, k->c[ax], lines, n, m, M, phase, out, acc, s);
 }
 
 static int convolve(paresis_fresnel_plan* p, const float2* wave_in, const paresis_fresnel_kernel* k, float2 phase, float2* wave_out,
@@ -295,7 +363,11 @@ extern "C" int paresis_fresnel_plan_create(int nx, int ny, int margin, paresis_f
     p->nxp = nx + 2 * margin; p->nyp = ny + 2 * margin;
     p->have_2d = false; p->buf = nullptr; p->spec = nullptr; p->work_bytes = 0;
     p->work = nullptr; p->mid = nullptr; p->zbuf = nullptr;
-    for (int ax = 0; ax < 2; ++ax) { p->own.g[ax] = p->own.c[ax] = nullptr; p->made_lines[ax] = p->made_zp[ax] = p->made_zm[ax] = false; }
+    for (int ax = 0; ax < 2; ++ax) {
+        p->own.g[ax] = p->own.c[ax] = p->own.g_dr[ax] = nullptr;
+        p->made_lines[ax] = p->made_zp[ax] = p->made_zm[ax] = false;
+        p->fused[ax] = false; p->tw[ax] = nullptr;
+    }
     p->len[0] = nx; p->len[1] = ny;
     cufftResult r = CUFFT_SUCCESS;
     size_t line_ws = 0;
@@ -305,14 +377,18 @@ extern "C" int paresis_fresnel_plan_create(int nx, int ny, int margin, paresis_f
         int M = p->fft_len[ax];
         const int batch = ax == 1 ? nx : ny;
         size_t ws = 0;
-        r = cufftCreate(&p->lines[ax]);
-        p->made_lines[ax] = r == CUFFT_SUCCESS;
-        if (r == CUFFT_SUCCESS) r = cufftMakePlanMany(p->lines[ax], 1, &M, nullptr, 1, M, nullptr, 1, M, CUFFT_C2C, batch, &ws);
-        line_ws += ws;
+        p->log_m[ax] = line_fft_log(M);
+        p->fused[ax] = p->log_m[ax] != 0;
+        if (!p->fused[ax]) {
+            r = cufftCreate(&p->lines[ax]);
+            p->made_lines[ax] = r == CUFFT_SUCCESS;
+            if (r == CUFFT_SUCCESS) r = cufftMakePlanMany(p->lines[ax], 1, &M, nullptr, 1, M, nullptr, 1, M, CUFFT_C2C, batch, &ws);
+            line_ws += ws;
+        }
         if (r == CUFFT_SUCCESS) { r = cufftPlan1d(&p->zp[ax], p->period[ax], CUFFT_Z2Z, 1); p->made_zp[ax] = r == CUFFT_SUCCESS; }
         if (r == CUFFT_SUCCESS) { r = cufftPlan1d(&p->zm[ax], M, CUFFT_Z2Z, 1); p->made_zm[ax] = r == CUFFT_SUCCESS; }
     }
-    const size_t work_elems = std::max((size_t)nx * p->fft_len[1], (size_t)ny * p->fft_len[0]);
+    const size_t work_elems = std::max((size_t)nx * (p->fused[1] ? ny : p->fft_len[1]), (size_t)ny * (p->fused[0] ? nx : p->fft_len[0]));
     const size_t z_elems = (size_t)std::max(p->period[0], p->period[1]) + (size_t)std::max(p->fft_len[0], p->fft_len[1]);
     cudaError_t e = cudaSuccess;
     if (r == CUFFT_SUCCESS) e = cudaMalloc(&p->work, sizeof(float2) * work_elems);
@@ -322,6 +398,23 @@ extern "C" int paresis_fresnel_plan_create(int nx, int ny, int margin, paresis_f
     if (r != CUFFT_SUCCESS) rc = fft_error(r, "cuFFT line plans");
     else if (e != cudaSuccess) rc = check_cuda(e, "cudaMalloc(fresnel work buffers)");
     else rc = kernel_alloc(p, &p->own);
+    for (int ax = 0; ax < 2 && rc == PARESIS_OK; ++ax) {
+        if (!p->fused[ax]) continue;
+        const int lm = p->log_m[ax], entries = fl_tw_entries(lm);
+        std::vector<float2> tw((size_t)entries);
+        for (int k = 0; k < fl_outer(lm); ++k) {          // pass k: S = M / 8^k, W = exp(-2 pi i / S), powers 1..4 of W^j
+            const int S = 1 << (lm - 3 * k);
+            float2* t = tw.data() + fl_tw_offset(lm, k);
+            for (int j = 0; j < S / 8; ++j)
+                for (int pw = 1; pw <= 4; ++pw) {
+                    const double a = -2.0 * 3.14159265358979323846 * (double)((long long)j * pw % S) / (double)S;
+                    t[4 * j + pw - 1] = make_float2((float)cos(a), (float)sin(a));
+                }
+        }
+        e = cudaMalloc(&p->tw[ax], sizeof(float2) * entries);
+        if (e == cudaSuccess) e = cudaMemcpy(p->tw[ax], tw.data(), sizeof(float2) * entries, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = check_cuda(e, "twiddle table");
+    }
     if (rc != PARESIS_OK) {
         paresis_fresnel_plan_destroy(p);
         return rc;
@@ -339,6 +432,7 @@ extern "C" int paresis_fresnel_plan_destroy(paresis_fresnel_plan* p) {
         if (p->made_zm[ax]) cufftDestroy(p->zm[ax]);
     }
     kernel_free(&p->own);
+    for (int ax = 0; ax < 2; ++ax) if (p->tw[ax]) cudaFree(p->tw[ax]);
     if (p->work) cudaFree(p->work);
     if (p->mid) cudaFree(p->mid);
     if (p->zbuf) cudaFree(p->zbuf);

@@ -291,11 +291,13 @@ def test_fresnel_propagation(abi, golden):
     plan.close()
 
 
-@pytest.mark.parametrize("shape,margin", [((96, 128), 15), ((70, 111), 15), ((129, 64), 7), ((50, 50), 0), ((300, 260), 16)])
+@pytest.mark.parametrize("shape,margin", [((96, 128), 15), ((70, 111), 15), ((129, 64), 7), ((50, 50), 0), ((300, 260), 16),
+                                          ((256, 512), 15), ((1000, 1300), 15), ((2048, 1024), 15)])
 def test_fresnel_separable_path_is_the_padded_transform(abi, shape, margin):
-    """The production propagator (per-axis circular convolution of period n + 2m through power-of-two line transforms plus the
-    reflect-margin terms, csrc/fresnel.cu) against numpy's literal pad -> fft2 -> transfer -> ifft2 -> crop (Experiment.py:236-251)
-    in fp64, and against the library's own literal chain (paresis_fresnel_spectrum / _from_spectrum)."""
+    """The production propagator (per-axis circular convolution of period n + 2m through line transforms plus the reflect-margin
+    terms, csrc/fresnel.cu; the larger shapes take the in-shared-memory transform of fresnel_lines.cuh at M = 512 ... 4096, the
+    others batched cuFFT) against numpy's literal pad -> fft2 -> transfer -> ifft2 -> crop (Experiment.py:236-251) in fp64, and
+    against the library's own literal chain (paresis_fresnel_spectrum / _from_spectrum)."""
     from paresis_b200 import hostmath as hm
     nx, ny = shape
     rng = np.random.default_rng(nx * 1000 + ny)
@@ -328,6 +330,32 @@ def test_fresnel_separable_path_is_the_padded_transform(abi, shape, margin):
         plan.from_spectrum(hx_d, hy_d, 1.0, lit, None)
         assert dist(lit.cpu().numpy(), want) < 2e-6
         kern.close()
+    plan.close()
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_fresnel_benchmark_grids_match_the_literal_chain(abi, n):
+    """M = 8192 and 16384 of the in-shared-memory line transform (the sizes bench.py times) against cuFFT's Bluestein transform
+    of the reference's (n + 30)^2 grid, on a field with the benchmark's dynamic range."""
+    from paresis_b200 import hostmath as hm
+    g = torch.Generator(device="cuda").manual_seed(n)
+    amp = 1.0 + 0.3 * torch.rand((n, n), device="cuda", generator=g)
+    ph = 6.0 * torch.rand((n, n), device="cuda", generator=g)
+    w_in = torch.polar(amp, ph).to(torch.complex64)
+    del amp, ph
+    plan = abi.FresnelPlan(n, n, 15)
+    hx, hy, phase = hm.fresnel_vectors(n, n, 15, (n, n), 0.75 * 4096 / n, 1.0, 52.0, 1.5)
+    hx_d, hy_d = dev(hx, torch.complex64), dev(hy, torch.complex64)
+    got = torch.empty_like(w_in)
+    plan.propagate(w_in, hx_d, hy_d, 1.0, got, None)
+    lit = torch.empty_like(w_in)
+    plan.spectrum(w_in)
+    plan.from_spectrum(hx_d, hy_d, 1.0, lit, None)
+    num = torch.linalg.vector_norm((got - lit).to(torch.complex128)).item()
+    den = torch.linalg.vector_norm(lit.to(torch.complex128)).item()
+    assert num / den < 3e-6, num / den
+    # intensities, the quantity the images are made of
+    assert rel_l2((got.abs() ** 2).cpu().numpy()[::7, ::5], (lit.abs() ** 2).cpu().numpy()[::7, ::5]) < 3e-6
     plan.close()
 
 
