@@ -618,15 +618,17 @@ def grid_8192(args, torch, shim, geometry, abi, ws, peak, flush):
 
 def fresnel_section(args, torch, shim, geometry, ws, peak):
     """BASELINE.json configs[3]: the Fresnel-propagator model (Experiment.py:279-405, wavePropagation :219-252) at 4096^2 and
-    8192^2, device time per membrane position (three propagations: reference beam, membrane->object, object->detector; the
-    first two share their forward transform).  Roofline entry of the propagation: >= 64 B per padded pixel (two 2-D
-    transforms, each two passes of read + write of complex64) against what it takes -- the transforms are cuFFT at the
-    reference's (N + 30)^2 size, 4126 = 2 x 2063 and 8222 = 2 x 4111: Bluestein (profiles/r02_fresnel_launches.txt)."""
+    8192^2, device time per membrane position (three propagations: reference beam, membrane->object, object->detector).
+    A propagation is two per-axis circular convolutions of period N + 30 (csrc/fresnel.cu): per axis one kernel that takes
+    a line through two power-of-two transforms in shared memory (fresnel_lines.cuh) and one that adds the reflect-margin
+    terms and transposes.  Roofline entry: the algorithmic traffic of that formulation, one read + one write of the complex
+    wave per kernel = 4 x 16 B per pixel and propagation, against the time of the whole position (which also holds the two
+    transmissions, the |.|^2 accumulation and the detector)."""
     if args.skip_extras:
         return None
     import contextlib
     import io
-    out = {"alg_bytes_per_padded_pixel_per_propagation": 64, "propagations_per_position": 3, "forward_transforms_per_position": 2,
+    out = {"alg_bytes_per_pixel_per_propagation": 64, "propagations_per_position": 3, "line_transform": "in shared memory, M = 2N",
            "peak_gbs": peak, "grids": {}}
     for n in (4096, 8192):
         with contextlib.redirect_stdout(io.StringIO()):
@@ -646,9 +648,8 @@ def fresnel_section(args, torch, shim, geometry, ws, peak):
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = float(np.median(times[1:]))
-        padded = float(n + 30) ** 2
-        gbs = 3 * 64.0 * padded / (ms * 1e-3) / 1e9
-        out["grids"][str(n)] = {"ms_per_position": ms, "positions_per_s": 1e3 / ms, "fft_size": n + 30,
+        gbs = 3 * 64.0 * float(n) ** 2 / (ms * 1e-3) / 1e9
+        out["grids"][str(n)] = {"ms_per_position": ms, "positions_per_s": 1e3 / ms, "period": n + 30, "line_transform_length": 2 * n,
                                 "achieved_gbs": gbs, "frac": gbs / peak}
         del eng, exp, scene
         geometry.drop_device_tables()

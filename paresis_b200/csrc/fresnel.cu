@@ -130,52 +130,61 @@ mul_lines_kernel(float2* __restrict__ work, const float2* __restrict__ G, int M)
 }
 
 // out[s][l] = (work[l][s] + margin terms) * phase for s < n, transposed through shared memory; the last pass can add
-// |.|^2 into acc instead of (or besides) storing the field.  32 lines x 32 samples per block of 32 x 8 threads; a thread
-// owns four lines of one sample.  MARGIN > 0: compile-time margin (the loop over the 2m terms unrolls, every shared-memory
-// offset is an immediate); MARGIN = 0: run-time margin m.
-constexpr int POST_T = 32, POST_MAXM = 16;
+// |.|^2 into acc instead of (or besides) storing the field.  32 lines x 64 samples per block of 32 x 8 threads; a thread
+// owns four lines (8 apart) of two samples (32 apart), so that one term costs two 128-bit broadcast loads of margin
+// samples and two kernel values for 32 FMAs.  MARGIN > 0: compile-time margin (the loop over the 2m terms unrolls, every
+// shared-memory offset is an immediate); MARGIN = 0: run-time margin m.
+constexpr int POST_L = 32, POST_S = 64, POST_MAXM = 16;
 template <int MARGIN>
 __global__ void __launch_bounds__(256)
 post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in, const float2* __restrict__ c, int lines, int n, int m_rt,
                   int pitch, float2 phase, float2* __restrict__ out, float* __restrict__ acc) {
-    __shared__ float2 tile[POST_T][POST_T + 1];
-    __shared__ float2 edge[2 * POST_MAXM][POST_T + 1];      // [term][line]: the four lines of a thread are 8 apart
-    __shared__ float2 cwin[POST_T + 2 * POST_MAXM];
+    __shared__ float2 tile[POST_L][POST_S + 1];
+    __shared__ __align__(16) float2 edge[2 * POST_MAXM][POST_L];   // [term][slot]: lines ty, ty+8 at slots 2ty, 2ty+1; ty+16, ty+24 at 16+2ty, 17+2ty
+    __shared__ float2 cwin[POST_S + 2 * POST_MAXM];
     const int m = MARGIN > 0 ? MARGIN : m_rt;
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POST_T + tx;
-    const int s0 = blockIdx.x * POST_T, l0 = blockIdx.y * POST_T;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int s0 = blockIdx.x * POST_S, l0 = blockIdx.y * POST_L;
     // the 2m samples of each line that the reflect margins repeat, and the kernel values this tile meets
-    for (int k = tid; k < POST_T * 2 * m; k += 256) {
+    for (int k = tid; k < POST_L * 2 * m; k += 256) {
         const int l = k / (2 * m), j = k - l * 2 * m;
         const int src = j < m ? j + 1 : n - 2 - (j - m);
-        edge[j][l] = l0 + l < lines ? in[(size_t)(l0 + l) * n + src] : make_float2(0.f, 0.f);
+        const int slot = (l & 16) + 2 * (l & 7) + ((l >> 3) & 1);
+        edge[j][slot] = l0 + l < lines ? in[(size_t)(l0 + l) * n + src] : make_float2(0.f, 0.f);
     }
-    for (int k = tid; k < POST_T + 2 * m; k += 256) cwin[k] = c[min(s0 + 1 + k, n + 2 * m - 1)];
+    for (int k = tid; k < POST_S + 2 * m; k += 256) cwin[k] = c[min(s0 + 1 + k, n + 2 * m - 1)];
     __syncthreads();
-    const int s = s0 + tx;
-    float2 v[POST_T / 8];
+    float2 v[4][2];
 #pragma unroll
-    for (int i = 0; i < POST_T / 8; ++i) {
-        const int l = l0 + ty + 8 * i;
-        v[i] = (s < n && l < lines) ? work[(size_t)l * pitch + s] : make_float2(0.f, 0.f);
-    }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = l0 + ty + 8 * i, s = s0 + tx + 32 * h;
+            v[i][h] = (s < n && l < lines) ? work[(size_t)l * pitch + s] : make_float2(0.f, 0.f);
+        }
     // term j < m: core[j + 1] c[s + j + 1];  term j >= m: core[n - 2 - (j - m)] c[s + 3m - j]
 #pragma unroll
     for (int j = 0; j < (MARGIN > 0 ? 2 * MARGIN : 2 * POST_MAXM); ++j) {
         if (MARGIN == 0 && j >= 2 * m) break;
-        const float2 cv = cwin[j < m ? tx + j : tx + 3 * m - j - 1];
+        const int ci = j < m ? tx + j : tx + 3 * m - j - 1;
+        const float2 cv[2] = {cwin[ci], cwin[ci + 32]};
+        const float4 ea = *reinterpret_cast<const float4*>(&edge[j][2 * ty]), eb = *reinterpret_cast<const float4*>(&edge[j][16 + 2 * ty]);
+        const float2 e[4] = {make_float2(ea.x, ea.y), make_float2(ea.z, ea.w), make_float2(eb.x, eb.y), make_float2(eb.z, eb.w)};
 #pragma unroll
-        for (int i = 0; i < POST_T / 8; ++i) {
-            const float2 e = edge[j][ty + 8 * i];
-            v[i].x = fmaf(e.x, cv.x, fmaf(-e.y, cv.y, v[i].x));
-            v[i].y = fmaf(e.x, cv.y, fmaf(e.y, cv.x, v[i].y));
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                v[i][h].x = fmaf(e[i].x, cv[h].x, fmaf(-e[i].y, cv[h].y, v[i][h].x));
+                v[i][h].y = fmaf(e[i].x, cv[h].y, fmaf(e[i].y, cv[h].x, v[i][h].y));
+            }
     }
 #pragma unroll
-    for (int i = 0; i < POST_T / 8; ++i) tile[ty + 8 * i][tx] = v[i];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) tile[ty + 8 * i][tx + 32 * h] = v[i][h];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < POST_T / 8; ++i) {
+    for (int i = 0; i < POST_S / 8; ++i) {
         const int so = s0 + ty + 8 * i, lo = l0 + tx;
         if (so < n && lo < lines) {
             const float2 w = tile[tx][ty + 8 * i];
@@ -294,8 +303,8 @@ static int kernel_fill(paresis_fresnel_plan* p, const float2* hx, const float2* 
 
 static int launch_post(dim3 grid, const float2* work, const float2* in, const float2* c, int lines, int n, int m, int pitch, float2 phase,
                        float2* out, float* acc, cudaStream_t s) {
-    if (m == 15) post_lines_kernel<15><<<grid, dim3(POST_T, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
-    else post_lines_kernel<0><<<grid, dim3(POST_T, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
+    if (m == 15) post_lines_kernel<15><<<grid, dim3(32, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
+    else post_lines_kernel<0><<<grid, dim3(32, 8), 0, s>>>(work, in, c, lines, n, m, pitch, phase, out, acc);
     PARESIS_LAUNCH_CHECK("post_lines_kernel");
     return PARESIS_OK;
 }
@@ -304,7 +313,7 @@ static int launch_post(dim3 grid, const float2* work, const float2* in, const fl
 static int convolve_axis(paresis_fresnel_plan* p, int ax, const float2* in, int lines, const paresis_fresnel_kernel* k, float2 phase,
                          float2* out, float* acc, cudaStream_t s) {
     const int n = p->len[ax], M = p->fft_len[ax], m = p->margin;
-    const dim3 gt((n + POST_T - 1) / POST_T, (lines + POST_T - 1) / POST_T);
+    const dim3 gt((n + POST_S - 1) / POST_S, (lines + POST_L - 1) / POST_L);
     if (p->fused[ax]) {
         int rc;
         switch (p->log_m[ax]) {
