@@ -11,3 +11,9 @@ python tools/one_position.py 3 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on --kernel-name 'regex:refract_|detect_tile|membrane_from_field' --launch-skip 4 -c 4 \
     -o gpurun_out/prof_final -f python tools/one_position.py 3 > gpurun_out/ncu_full_final.log 2>&1
 tail -1 gpurun_out/ncu_full_final.log
+# Fresnel model: launch list of two positions at 4096^2 and one full capture of its two kernels
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/fresnel_launches_final.csv \
+    python tools/fresnel_probe.py 4096 2 > gpurun_out/ncu_fresnel_launches.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name 'regex:line_convolve|post_lines' --launch-skip 8 -c 2 \
+    -o gpurun_out/prof_fresnel_final -f python tools/fresnel_probe.py 4096 2 > gpurun_out/ncu_fresnel_full.log 2>&1
+tail -1 gpurun_out/ncu_fresnel_full.log
