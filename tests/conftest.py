@@ -29,6 +29,10 @@ def golden():
     return load
 
 
+# PARESIS_REPORT_L2=<file>: resolved here, against the directory pytest was started from -- the workspace fixtures chdir
+_REPORT_L2 = os.path.abspath(os.environ["PARESIS_REPORT_L2"]) if os.environ.get("PARESIS_REPORT_L2") else None
+
+
 def rel_l2(a, b):
     import numpy as np
 
@@ -36,8 +40,8 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b.ravel())
     val = float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
-    if os.environ.get("PARESIS_REPORT_L2"):       # parity report: every measured distance, with its call site
+    if _REPORT_L2:       # parity report: every measured distance, with its call site
         fr = sys._getframe(1)
-        with open(os.environ["PARESIS_REPORT_L2"], "a") as fh:
+        with open(_REPORT_L2, "a") as fh:
             fh.write("%s:%d %s %.3e\n" % (os.path.basename(fr.f_code.co_filename), fr.f_lineno, fr.f_code.co_name, val))
     return val

@@ -2,7 +2,7 @@
 # Round-end evidence on the GPU box: full GPU test suite, default bench line, ncu launch list of the bench command,
 # one full ncu capture of a steady-state position (each ncu pass only after its command ran clean without ncu).
 set -o pipefail
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; tail -4 gpurun_out/pytest_gpu_final.log
 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err || { echo "bench failed"; tail -5 gpurun_out/bench_default.err; exit 1; }
 tail -c 600 gpurun_out/bench_default.log; echo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_final.csv \
