@@ -319,7 +319,8 @@ int paresis_fresnel_propagate(paresis_fresnel_plan* plan, const paresis_c32* wav
 
 /* The same in two steps, for a transfer function that is used more than once (every membrane position of a scan uses
  * the same distances and energies): paresis_fresnel_kernel_create turns (hx, hy) into the convolution kernels of both
- * axes (fp64 on the device, a few small launches on `stream`), paresis_fresnel_convolve propagates with them. */
+ * axes (fp64 on the device, a few small launches on `stream`), paresis_fresnel_convolve propagates with them.  A kernel
+ * belongs to plans of the size it was created with (anything else is PARESIS_ERR_ARG); it outlives the plan. */
 int paresis_fresnel_kernel_create(paresis_fresnel_plan* plan, const paresis_c32* hx, const paresis_c32* hy, paresis_stream stream,
                                   paresis_fresnel_kernel** kernel);
 int paresis_fresnel_kernel_destroy(paresis_fresnel_kernel* kernel);

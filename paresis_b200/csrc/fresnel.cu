@@ -10,10 +10,14 @@
 //          + sum_{t=1..m} core[t] c[s + t]                  (left reflect margin,  x_pad[m - t] = core[t])
 //          + sum_{u=0..m-1} core[N-2-u] c[s + 2m - u]       (right reflect margin, x_pad[m + N + u] = core[N-2-u])
 // The first sum is a linear convolution that fits a transform of size M >= 2N - 1 -- a power of two (2N) at the
-// benchmark grids: zero-pad, cuFFT (batched 1-D, in place), multiply by G = FFT_M(c arranged on [-(N-1), N-1]),
-// cuFFT back, and the 2m margin terms are added where the line is read back.  That is two power-of-two transforms per
-// axis and propagation instead of two Bluestein 2-D transforms; the result is the same circular convolution (no
-// truncation of the kernel, no change of the period), the kernels c and G are formed in fp64 on the device.
+// benchmark grids; the 2m margin terms are added in closed form where the line is read back.  The result is the same
+// circular convolution (no truncation of the kernel, no change of the period); c and G = FFT_M(c arranged on
+// [-(N-1), N-1]) are formed in fp64 on the device, once per transfer function.  Per axis:
+//   * M a power of two in 512 .. 16384 (and within 1.5x of the next 7-smooth length): line_convolve_kernel
+//     (fresnel_lines.cuh) takes a line through both transforms and the multiply in shared memory;
+//   * otherwise: pad_lines_kernel, batched 1-D cuFFT in place, mul_lines_kernel, cuFFT back;
+//   then post_lines_kernel adds the margin terms, applies the global phase, accumulates |.|^2 and writes transposed, so
+//   that the second axis is a row pass again.
 // paresis_fresnel_spectrum / _from_spectrum keep the literal pad -> fft2 -> transfer -> ifft2 -> crop chain.
 #include <cufft.h>
 
@@ -28,6 +32,7 @@ struct paresis_fresnel_kernel {
     float2* g[2];     // [0]: along x (lines of the second pass, M_x values), [1]: along y
     float2* c[2];     // the spatial kernels, P_x / P_y values
     float2* g_dr[2];  // g in the digit-reversed, pair-major order of the in-shared-memory transform (axes that use it)
+    int len[2], fft_len[2];   // the plan geometry the kernel was prepared for
 };
 
 struct paresis_fresnel_plan {
@@ -261,7 +266,7 @@ static int fft_error(cufftResult r, const char* what) {
 }
 
 static int kernel_alloc(const paresis_fresnel_plan* p, paresis_fresnel_kernel* k) {
-    for (int ax = 0; ax < 2; ++ax) { k->g[ax] = nullptr; k->c[ax] = nullptr; k->g_dr[ax] = nullptr; }
+    for (int ax = 0; ax < 2; ++ax) { k->g[ax] = nullptr; k->c[ax] = nullptr; k->g_dr[ax] = nullptr; k->len[ax] = p->len[ax]; k->fft_len[ax] = p->fft_len[ax]; }
     for (int ax = 0; ax < 2; ++ax) {
         PARESIS_CUDA(cudaMalloc(&k->g[ax], sizeof(float2) * p->fft_len[ax]));
         PARESIS_CUDA(cudaMalloc(&k->c[ax], sizeof(float2) * p->period[ax]));
@@ -480,6 +485,12 @@ extern "C" int paresis_fresnel_convolve(paresis_fresnel_plan* p, const paresis_c
         set_last_error("paresis_fresnel_convolve: null pointer");
         return PARESIS_ERR_ARG;
     }
+    for (int ax = 0; ax < 2; ++ax)
+        if (kernel->len[ax] != p->len[ax] || kernel->fft_len[ax] != p->fft_len[ax]) {
+            set_last_error("paresis_fresnel_convolve: the kernel was prepared for a %d x %d plan, this one is %d x %d", kernel->len[0],
+                           kernel->len[1], p->len[0], p->len[1]);
+            return PARESIS_ERR_ARG;
+        }
     return convolve(p, (const float2*)wave_in, kernel, make_float2(phase.re, phase.im), (float2*)wave_out, intensity_acc, (cudaStream_t)stream);
 }
 

@@ -329,6 +329,12 @@ def test_fresnel_separable_path_is_the_padded_transform(abi, shape, margin):
         plan.spectrum(w_in)
         plan.from_spectrum(hx_d, hy_d, 1.0, lit, None)
         assert dist(lit.cpu().numpy(), want) < 2e-6
+        if (nx, ny) == (96, 128):      # a kernel only fits plans of its own size
+            other = abi.FresnelPlan(64, 128, margin)
+            with pytest.raises(RuntimeError, match="prepared for a 96 x 128 plan"):
+                other.convolve(torch.zeros((64, 128), device="cuda", dtype=torch.complex64), kern, 1.0,
+                               torch.empty((64, 128), device="cuda", dtype=torch.complex64), None)
+            other.close()
         kern.close()
     plan.close()
 
