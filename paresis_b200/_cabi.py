@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libparesis_b200.so")
+# PARESIS_B200_LIB: another build of the same library in the package directory (the bounds-checked debug build)
+LIB_PATH = os.path.join(_PKG, os.path.basename(os.environ.get("PARESIS_B200_LIB", "libparesis_b200.so")))
 
 OK = 0
 FLAG_NONFINITE = 1

@@ -1,8 +1,10 @@
 """Build the CUDA library in-tree: nvcc, sm_100a only, C ABI, no torch headers.
 
-    python -m paresis_b200.build [--force] [--verbose]
+    python -m paresis_b200.build [--force] [--verbose] [--bounds-check]
 
-The resulting ``paresis_b200/libparesis_b200.so`` is git-ignored but travels with the tree.
+The resulting ``paresis_b200/libparesis_b200.so`` is git-ignored but travels with the tree.  ``--bounds-check`` builds
+``libparesis_b200_checked.so`` instead (-DPARESIS_BOUNDS_CHECK: device asserts on the shared-memory and queue indices of the
+newer kernels); ``PARESIS_B200_LIB=libparesis_b200_checked.so`` makes the binding load it.
 """
 import glob
 import os
@@ -36,14 +38,15 @@ def _headers():
     return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "paresis_b200.h")]
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, bounds_check=False):
     """Compile every .cu to an object (in parallel, only the stale ones) and link the shared library."""
-    if not force and not _stale():
+    lib = os.path.join(PKG, "libparesis_b200_checked.so") if bounds_check else LIB
+    if not force and not bounds_check and not _stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(CSRC, "_obj")
+    objdir = os.path.join(CSRC, "_obj_checked" if bounds_check else "_obj")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")]
+    flags = [f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")] + (["-DPARESIS_BOUNDS_CHECK"] if bounds_check else [])
     newest_header = max(os.path.getmtime(h) for h in _headers())
 
     def compile_one(src):
@@ -59,10 +62,10 @@ def build_library(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
     # --cudart shared: the runtime is the image's libcudart.so, not a private static copy inside the library
-    cmd = [NVCC, "-shared", "--cudart", "shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    cmd = [NVCC, "-shared", "--cudart", "shared", "-o", lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, bounds_check="--bounds-check" in sys.argv))

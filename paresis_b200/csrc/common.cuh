@@ -29,6 +29,15 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 #define PARESIS_LAUNCH_CHECK(name) PARESIS_CUDA(cudaPeekAtLastError())
 
+// Index checks of the debug build (python -m paresis_b200.build --bounds-check -> libparesis_b200_checked.so, selected with
+// PARESIS_B200_LIB): a device assert traps on the first index outside [0, n).  Nothing in the production library.
+#ifdef PARESIS_BOUNDS_CHECK
+#include <assert.h>
+#define PARESIS_BOUND(i, n) assert((long long)(i) >= 0 && (long long)(i) < (long long)(n))
+#else
+#define PARESIS_BOUND(i, n) ((void)0)
+#endif
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // Streaming loads: every map on this path is read once per kernel, keep it out of L1.

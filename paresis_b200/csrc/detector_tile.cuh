@@ -118,7 +118,10 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
                     float4 v[BATCH];
 #pragma unroll
                     for (int b = 0; b < BATCH; ++b)
-                        if (r0 + b < T::NR) v[b] = __ldg(reinterpret_cast<const float4*>(base + rowoff[min(u_lo * OS + r0 + b, T::SWX - 1)]));
+                        if (r0 + b < T::NR) {
+                            PARESIS_BOUND(rowoff[min(u_lo * OS + r0 + b, T::SWX - 1)] + ya + 4 * cg + 3, nx * ny);
+                            v[b] = __ldg(reinterpret_cast<const float4*>(base + rowoff[min(u_lo * OS + r0 + b, T::SWX - 1)]));
+                        }
 #pragma unroll
                     for (int b = 0; b < BATCH; ++b) {
                         const int r = r0 + b;
@@ -300,6 +303,7 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
                 const int n = (ok0 ? 0 : 1) + (ok1 ? 0 : 1);
                 int slot = atomicAdd(&n_queued, n);
                 const unsigned local = (unsigned)((al + k) * DT_TY + 2 * lane);
+                PARESIS_BOUND(slot + n - 1, DT_TX * DT_TY);
                 if (!ok0) qa[slot++] = make_uint4(local, __float_as_uint(acc[k].x), r[0], r[1]);
                 if (!ok1) qa[slot] = make_uint4(local + 1u, __float_as_uint(acc[k].y), r[2], r[3]);
             }
@@ -312,6 +316,7 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
         const int nq = n_queued;
         for (int qi = tid; qi < nq; qi += DT_THREADS) {
             const uint4 e = qa[qi];
+            PARESIS_BOUND(e.x, DT_TX * DT_TY); PARESIS_BOUND(a0 + e.x / DT_TY, det_x); PARESIS_BOUND(b0 + e.x % DT_TY, det_y);
             const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
             const float lam = __uint_as_float(e.y);
             float x;
@@ -340,7 +345,11 @@ detect_tile_kernel(DetImages im, int nx, int ny, int det_x, int det_y, const flo
             const size_t p = (size_t)(a0 + e.x / DT_TY) * det_y + (b0 + e.x % DT_TY);
             float x;
             if (poisson_block(__int_as_float(e.y), seed, seq, p, blk, x)) out[p] = x;
-            else qnext[atomicAdd(nnext, 1)] = e;       // at most nq <= QB_CAP entries
+            else {
+                const int slot = atomicAdd(nnext, 1);   // at most nq <= QB_CAP entries
+                PARESIS_BOUND(slot, T::QB_CAP);
+                qnext[slot] = e;
+            }
         }
         int2* tq = qcur; qcur = qnext; qnext = tq;
         int* tn = ncur; ncur = nnext; nnext = tn;

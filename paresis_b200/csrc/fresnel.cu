@@ -155,6 +155,7 @@ post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in
         const int l = k / (2 * m), j = k - l * 2 * m;
         const int src = j < m ? j + 1 : n - 2 - (j - m);
         const int slot = (l & 16) + 2 * (l & 7) + ((l >> 3) & 1);
+        PARESIS_BOUND(j, 2 * POST_MAXM); PARESIS_BOUND(slot, POST_L); PARESIS_BOUND(src, n);
         edge[j][slot] = l0 + l < lines ? in[(size_t)(l0 + l) * n + src] : make_float2(0.f, 0.f);
     }
     for (int k = tid; k < POST_S + 2 * m; k += 256) cwin[k] = c[min(s0 + 1 + k, n + 2 * m - 1)];
@@ -172,6 +173,7 @@ post_lines_kernel(const float2* __restrict__ work, const float2* __restrict__ in
     for (int j = 0; j < (MARGIN > 0 ? 2 * MARGIN : 2 * POST_MAXM); ++j) {
         if (MARGIN == 0 && j >= 2 * m) break;
         const int ci = j < m ? tx + j : tx + 3 * m - j - 1;
+        PARESIS_BOUND(ci, POST_S + 2 * POST_MAXM - 32); PARESIS_BOUND(ci + 32, POST_S + 2 * m);
         const float2 cv[2] = {cwin[ci], cwin[ci + 32]};
         const float4 ea = *reinterpret_cast<const float4*>(&edge[j][2 * ty]), eb = *reinterpret_cast<const float4*>(&edge[j][16 + 2 * ty]);
         const float2 e[4] = {make_float2(ea.x, ea.y), make_float2(ea.z, ea.w), make_float2(eb.x, eb.y), make_float2(eb.z, eb.w)};

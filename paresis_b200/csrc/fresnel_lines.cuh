@@ -110,6 +110,8 @@ __device__ __forceinline__ void pass_forward(float2* line, const float2* __restr
         const int b = b0 + tid;
         const int j = b & (Q - 1), base = ((b >> LOG_Q) << LOG_S) + j;
         float2* const p = line + fl_pad(base);
+        PARESIS_BOUND(fl_pad(base) + 7 * Q + ((7 * Q) >> 4), (1 << LOG_M) + (1 << (LOG_M - 4)) + 16);
+        PARESIS_BOUND(fl_pad(base) + 7 * Q + ((7 * Q) >> 4) - fl_pad(base + 7 * Q), 1);      // the closed form IS fl_pad
         float2 v[8];
         if (FROM_GLOBAL) {
 #pragma unroll
@@ -136,6 +138,8 @@ __device__ __forceinline__ void pass_inverse(float2* line, float2* __restrict__ 
         const int b = b0 + tid;
         const int j = b & (Q - 1), base = ((b >> LOG_Q) << LOG_S) + j;
         const float2* const p = line + fl_pad(base);
+        PARESIS_BOUND(fl_pad(base) + 7 * Q + ((7 * Q) >> 4), (1 << LOG_M) + (1 << (LOG_M - 4)) + 16);
+        PARESIS_BOUND(fl_pad(base) + 7 * Q + ((7 * Q) >> 4) - fl_pad(base + 7 * Q), 1);
         float2 w[8];
         fl_twiddles(tw + 4 * j, w);
         float2 v[8];
@@ -164,6 +168,9 @@ __device__ __forceinline__ void pass_middle(float2* line, const float4* __restri
         const int b = b0 + tid;
         if (GROUPS < THREADS && b >= GROUPS) break;
         float2* const p = line + b * R + ((b * R) >> 4);      // R <= 16: a group never straddles a padding slot
+        PARESIS_BOUND(b * R + ((b * R) >> 4) + R - 1, (1 << LOG_M) + (1 << (LOG_M - 4)) + 16);
+        PARESIS_BOUND(fl_pad(b * R + R - 1) - (b * R + ((b * R) >> 4) + R - 1), 1);
+        PARESIS_BOUND((R / 2 - 1) * GROUPS + b, 1 << (LOG_M - 1));
         float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = p[q];
