@@ -501,6 +501,7 @@ def energy_sharded(args, torch, dist, shim, geometry, abi, rank, world, ws):
     exp.myDetector.det_param["myBinsThersholds"] = []
     thresholds = list(exp._open_bins(0))
     reduce_events = []
+    pending = [None]
 
     def job(rep):
         np.random.seed(777 + rep)                                # the same membrane positions on every rank
@@ -509,8 +510,15 @@ def energy_sharded(args, torch, dist, shim, geometry, abi, rank, world, ws):
                 # the membrane of this position, cut on every rank (no host copy of the map: nobody saves it here)
                 mem.myGeometry, _ = geometry.membrane_segmented(mem, n, n, mem.membranePixelSize, point, mem.myPMMAThickness)
                 scene = exp._scene(thresholds)
-                shard.compute_rt_energy_sharded(eng, scene, point, owner=0, sequence_base=rep * positions,
-                                                reduce_events=reduce_events if rep >= 0 else None)
+                # the host-side tail of a position (means + NaN guard: an all_reduce and a device->host read) is taken
+                # after the NEXT position has been queued
+                nxt = shard.compute_rt_energy_sharded(eng, scene, point, owner=0, sequence_base=rep * positions,
+                                                      reduce_events=reduce_events if rep >= 0 else None, defer=True)
+                if pending[0] is not None:
+                    pending[0].finish()
+                pending[0] = nxt
+            pending[0].finish()
+            pending[0] = None
 
     def barrier():
         torch.cuda.synchronize()

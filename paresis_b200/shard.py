@@ -45,12 +45,40 @@ def combine_means(values, indices, n_total, group=None):
     return full
 
 
-def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, sequence_base=0, reduce_events=None):
+class ShardedPosition:
+    """What ``compute_rt_energy_sharded(..., defer=True)`` returns on every rank: the device work of the position is
+    queued, its host-side tail is not done yet.  ``finish()`` waits for the per-energy means and the status flags (one
+    all_reduce, already queued), raises ``InsaneValues`` on every rank if any rank saw a non-finite value, and returns what
+    the immediate call returns (the result dict on the owner, None elsewhere).  The images must not be used before it."""
+
+    def __init__(self, out, tail_host, ready, work, spectrum, is_owner):
+        self._out, self._tail, self._ready, self._work = out, tail_host, ready, work
+        self._spectrum, self._is_owner, self._done = spectrum, is_owner, False
+
+    def finish(self):
+        if not self._done:
+            self._ready.synchronize()
+            self._done = True
+            tail = self._tail.numpy()
+            if tail[-1] != 0:
+                from .engine import InsaneValues
+                raise InsaneValues("The calculated intensity refractive includes some nans or insane values")
+            if self._is_owner:
+                m = tail[:-1]
+                energies = np.array([e for e, _ in self._spectrum])
+                self._out["mean_energy"] = (float(np.dot(m, energies)), float(m.sum()))
+        return self._out if self._is_owner else None
+
+
+def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, sequence_base=0, reduce_events=None, defer=False):
     """One membrane position with the spectrum spread over the ranks of ``group``.
 
     Every rank calls this with the same scene.  Returns, on ``owner``, the dict that
     ``ImageFormation.compute_rt`` returns (device tensors + mean_energy); None elsewhere.
-    ``reduce_events``: a list that receives one (start, end) CUDA event pair per NCCL reduction (bench.py)."""
+    ``reduce_events``: a list that receives one (start, end) CUDA event pair per NCCL reduction (bench.py).
+    ``defer=True``: return a ``ShardedPosition`` instead, without waiting for the device: the caller queues the next
+    position first and calls ``finish()`` on this one afterwards (every rank, same order), so the host's turn-around and
+    the device->host read of the means overlap the next position's kernels."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     first = point_num == 0
@@ -95,6 +123,15 @@ def compute_rt_energy_sharded(engine, scene, point_num, owner=0, group=None, seq
     # value: the status flags travel with the means (one all_reduce), every rank clears its own and every rank raises
     tail = torch.cat((means, engine.flag.to(torch.float64)))
     engine.flag.zero_()
+    if defer:
+        work = dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=group, async_op=True) if world > 1 else None
+        if work is not None:
+            work.wait()                         # orders the copy below after the collective on this stream; the host goes on
+        host = torch.empty(tail.shape, dtype=tail.dtype, pin_memory=True)
+        host.copy_(tail, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        return ShardedPosition(out, host, ready, work, scene.spectrum, rank == owner)
     if world > 1:
         dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=group)
     tail = tail.cpu().numpy()

@@ -50,6 +50,18 @@ def test_world1_matches_single_call(noise):
                 # energy by energy through the lean hop kernel: two fixed-point roundings of the same deposits)
                 assert rel_l2(a, b) < 3e-6, k
         assert np.allclose(got["mean_energy"], ref["mean_energy"], rtol=1e-7)     # fp32 partial sums of the reference beam: the miss list is drained in arrival order
+        # the deferred form: same images, same means, once finish() has been called
+        later = shard.compute_rt_energy_sharded(eng, scene, point, defer=True)
+        assert "mean_energy" not in later._out
+        fin = later.finish()
+        assert fin is later.finish()
+        for k in ("sample", "reference"):
+            a, b = fin[k].cpu().numpy(), got[k].cpu().numpy()
+            if noise:
+                assert np.mean(a != b) < 2e-3 and rel_l2(a, b) < 1e-3, k
+            else:
+                assert rel_l2(a, b) < 3e-6, k          # fp32 REDs of the miss list commit in any order
+        assert np.allclose(fin["mean_energy"], got["mean_energy"], rtol=1e-7)
 
 
 def _rank_main(rank, world, port, q):
@@ -62,6 +74,13 @@ def _rank_main(rank, world, port, q):
     out = {}
     for point in (0, 1):
         res = shard.compute_rt_energy_sharded(eng, scene, point)
+        later = shard.compute_rt_energy_sharded(eng, scene, point, defer=True).finish()      # every rank, same order
+        if rank == 0:
+            for k in ("sample", "reference"):
+                assert float((later[k] != res[k]).float().mean()) < 2e-3, k
+            assert np.allclose(later["mean_energy"], res["mean_energy"], rtol=1e-7)
+        else:
+            assert later is None
         if rank == 0:
             single = eng.compute_rt(scene, point)
             out[point] = ({k: res[k].cpu().numpy() for k in ("sample", "reference")},
