@@ -453,7 +453,8 @@ class ImageFormation:
             self._waves = [torch.empty((self.nx, self.ny), **c64) for _ in range(2)]
 
     def _transfer(self, scene, distance, energy, magnification):
-        key = (distance, energy, magnification)
+        # everything the transfer function depends on (Experiment.py:243-250): the cache outlives a scene
+        key = (distance, energy, magnification, tuple(int(v) for v in scene.study_dims), float(scene.study_pixel_um))
         if key not in self._vectors:
             hx, hy, phase = hm.fresnel_vectors(self.nx, self.ny, 15, scene.study_dims, scene.study_pixel_um,
                                                distance, energy, magnification)
