@@ -170,8 +170,8 @@ def _worker_run(args):
     return _oracle_position(_worker_ctx, point, seed)
 
 
-def cpu_baseline_single(positions=(0, 1, 2)):
-    """Scalar port on one core: image-sets/s over a bounded sample of the workload."""
+def cpu_baseline_single(positions=tuple(range(8))):
+    """Scalar port on one core: image-sets/s over a bounded sample of the workload (8 positions: 10-15 s of CPU work)."""
     ctx = _oracle_setup()
     _oracle_position(ctx, 1, 999)
     t0 = time.perf_counter()
