@@ -68,7 +68,7 @@ PER_LAUNCH = 0   # > 1: that many positions share each kernel launch (blockIdx.z
 
 def config_dict(**extra):
     c = {"workload": WORKLOAD, "experiment": EXPERIMENT, "positions_per_step": POSITIONS * JOBS_PER_STEP, "positions_per_job": POSITIONS,
-         "grid": 2048, "energies": 1, "model": "RayT"}
+         "grid": 2048, "energies": 1, "propagation": "ray tracing (RayT)"}
     c.update(extra)
     return c
 
