@@ -363,6 +363,19 @@ def test_fresnel_benchmark_grids_match_the_literal_chain(abi, n):
     # intensities, the quantity the images are made of
     assert rel_l2((got.abs() ** 2).cpu().numpy()[::7, ::5], (lit.abs() ** 2).cpu().numpy()[::7, ::5]) < 3e-6
     plan.close()
+    if n == 4096:
+        # ... and against the literal chain in float64 on the host (Experiment.py:236-251), the whole 4126^2 transform
+        del lit
+        wave = w_in.cpu().numpy().astype(np.complex128)
+        spec = np.fft.fft2(np.pad(wave, 15, mode="reflect"))
+        del wave
+        spec *= hx.astype(np.complex128)[:, None]
+        spec *= hy.astype(np.complex128)[None, :]
+        want = (np.fft.ifft2(spec) * float(spec.shape[0] * spec.shape[1]))[15:15 + n, 15:15 + n]     # the vectors carry 1/(Px Py)
+        del spec
+        g = got.cpu().numpy()
+        assert float(np.linalg.norm(g - want) / np.linalg.norm(want)) < 3e-6
+        assert rel_l2(np.abs(g) ** 2, np.abs(want) ** 2) < 3e-6
 
 
 def test_detection(abi, golden):
