@@ -62,7 +62,8 @@ def build_library(force=False, verbose=False, bounds_check=False):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
     # --cudart shared: the runtime is the image's libcudart.so, not a private static copy inside the library
-    cmd = [NVCC, "-shared", "--cudart", "shared", "-o", lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    # the arch on the link line too: without it nvcc embeds an (empty) cubin of its default architecture, sm_52
+    cmd = [NVCC, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return lib
 
