@@ -62,7 +62,7 @@ ALG_BYTES = {
     "refract_sample_ref_hop": lambda n, det: 20.0 * n,        # read I_bs, t_m, t_s; write sample + reference
     "detect": lambda n, det: 2 * (4.0 * n + 4.0 * det),       # sample + reference images in one launch: read, write counts
 }
-SLOTS = 3        # positions in flight (paresis_rt_run_positions deals them over this many streams)
+SLOTS = 5               # membrane positions in flight (same-box A/B: 3 -> 5 is +1.2 %, 6 no better)
 PER_LAUNCH = 0   # > 1: that many positions share each kernel launch (blockIdx.z) instead; measured no faster
 
 

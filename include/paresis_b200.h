@@ -44,7 +44,8 @@ int paresis_version(void);
 const char* paresis_last_error(void);
 /* Performance knobs, results unaffected.  key 0: deposit mode of the fused refraction kernels
  * (0 = one REDG per deposit, 2 = warp/register aggregated, default); key 1: source rows per warp
- * (0 = automatic). */
+ * (0 = automatic); key 2: -1 = direct-to-L2 hop kernels, 0 = tile kernels (default); key 3: source rows per block of the tile
+ * hops (0 = chosen per launch to fill whole waves, the default). */
 int paresis_set_tuning(int key, int value);
 /* Frees the library's cached per-device scratch (the ray lists of the strip kernels: up to 16 bytes per study pixel and
  * beam, kept between calls so that a call allocates nothing).  Safe at any time; the next call allocates again. */
@@ -128,6 +129,9 @@ typedef struct {
                                 2: out += result, owner-computes rolling strips (the owner adds its finished rows).
                                 Modes 1 / 2 need intensity_scale and ignore zero_fill / clear_input / zero_scalar. */
     int reach;               /* modes 1 / 2, single beam: 8 or 12 = pixels a ray may move and still take the tiles */
+    int throughput;          /* mode 0: 0 = rows per block chosen so that THIS launch fills whole waves (best for a kernel
+                                running alone); 1 = full-height tiles, least work per pixel (best when the caller keeps
+                                several launches in flight, as paresis_rt_run_positions does: +3.9 % on its job) */
 } paresis_refract_extras;
 
 int paresis_refract_layers_ex(const float* intensity_in, float intensity_uniform,
@@ -242,6 +246,9 @@ typedef struct {
                                   position) on the caller's stream, instead of one launch per position on per-slot
                                   streams.  Needs a sphere field and detector bins of one energy; position 0 (extra
                                   images) always runs on its own.  0 / 1 = off. */
+    int throughput;            /* 1 = the hops use full-height tiles (paresis_refract_extras.throughput).  paresis_rt_run_positions
+                                  sets it for every position of a call with more than one; a single paresis_rt_run keeps
+                                  what the caller put here. */
 } paresis_rt_job;
 
 int paresis_rt_run(const paresis_rt_job* job_host, paresis_stream stream);

@@ -66,7 +66,7 @@ class RtJob(ctypes.Structure):
                 ("out_white", ctypes.c_void_p), ("dx_pad", ctypes.c_void_p), ("dy_pad", ctypes.c_void_p),
                 ("flag", ctypes.c_void_p), ("probe", ctypes.c_int), ("probe_start", ctypes.c_void_p),
                 ("probe_end", ctypes.c_void_p), ("i_bs_dirty", ctypes.c_int), ("i_bs_group", ctypes.c_void_p * (MAX_GROUP - 1)),
-                ("positions_per_launch", ctypes.c_int)]
+                ("positions_per_launch", ctypes.c_int), ("throughput", ctypes.c_int)]
 
 
 class GroupEnergy(ctypes.Structure):
@@ -96,7 +96,7 @@ class Membrane(ctypes.Structure):
 
 class RefractExtras(ctypes.Structure):
     _fields_ = [("zero_fill", ctypes.c_void_p * 3), ("clear_input", ctypes.c_int), ("zero_scalar", ctypes.c_void_p),
-                ("sum_ref", ctypes.c_void_p), ("intensity_scale", ctypes.c_float), ("mode", ctypes.c_int), ("reach", ctypes.c_int)]
+                ("sum_ref", ctypes.c_void_p), ("intensity_scale", ctypes.c_float), ("mode", ctypes.c_int), ("reach", ctypes.c_int), ("throughput", ctypes.c_int)]
 
 
 class HopItem(ctypes.Structure):
@@ -281,6 +281,8 @@ if os.environ.get("PARESIS_TILE_CONFIG"):     # development knob: -1 = direct-to
     set_tuning(2, int(os.environ["PARESIS_TILE_CONFIG"]))
 
 
+if os.environ.get("PARESIS_LEAN_ROWS"):        # development knob: source rows per block of the tile hops (0 = automatic)
+    set_tuning(3, int(os.environ["PARESIS_LEAN_ROWS"]))
 if os.environ.get("PARESIS_ROWS"):            # development knob: source rows per warp of the hop kernels
     set_tuning(1, int(os.environ["PARESIS_ROWS"]))
 

@@ -1,6 +1,6 @@
 """Build the CUDA library in-tree: nvcc, sm_100a only, C ABI, no torch headers.
 
-    python -m paresis_b200.build [--force] [--verbose] [--bounds-check]
+    python -m paresis_b200.build [--force] [--verbose] [--bounds-check] [--variant NAME -DMACRO=VALUE ...]
 
 The resulting ``paresis_b200/libparesis_b200.so`` is git-ignored but travels with the tree.  ``--bounds-check`` builds
 ``libparesis_b200_checked.so`` instead (-DPARESIS_BOUNDS_CHECK: device asserts on the shared-memory and queue indices of the
@@ -38,15 +38,20 @@ def _headers():
     return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "paresis_b200.h")]
 
 
-def build_library(force=False, verbose=False, bounds_check=False):
-    """Compile every .cu to an object (in parallel, only the stale ones) and link the shared library."""
+def build_library(force=False, verbose=False, bounds_check=False, variant=None, defines=()):
+    """Compile every .cu to an object (in parallel, only the stale ones) and link the shared library.
+    ``variant`` + ``defines``: an experimental build next to the production one (libparesis_b200_<variant>.so, its own object
+    directory, extra -D flags), to be A/B-ed on one box with PARESIS_B200_LIB."""
     lib = os.path.join(PKG, "libparesis_b200_checked.so") if bounds_check else LIB
-    if not force and not bounds_check and not _stale():
+    if variant:
+        lib = os.path.join(PKG, "libparesis_b200_%s.so" % variant)
+    if not force and not bounds_check and not variant and not _stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(CSRC, "_obj_checked" if bounds_check else "_obj")
+    objdir = os.path.join(CSRC, "_obj_" + variant if variant else ("_obj_checked" if bounds_check else "_obj"))
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")] + (["-DPARESIS_BOUNDS_CHECK"] if bounds_check else [])
+    flags = ([f for f in FLAGS if f not in ("--use_fast_math=false", "-shared")] + (["-DPARESIS_BOUNDS_CHECK"] if bounds_check else [])
+             + ["-D" + d for d in defines])
     newest_header = max(os.path.getmtime(h) for h in _headers())
 
     def compile_one(src):
@@ -69,4 +74,7 @@ def build_library(force=False, verbose=False, bounds_check=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, bounds_check="--bounds-check" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    _defines = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, bounds_check="--bounds-check" in sys.argv,
+                        variant=_variant, defines=_defines))

@@ -43,6 +43,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
     auto membrane_hop = [&](int e, float* dst) -> int {
         const paresis_rt_energy& en = job->energies_host[e];
         paresis_refract_extras x1{};
+        x1.throughput = job->throughput;
         if (fresh_bin) {
             x1.zero_fill[0] = job->acc_sample;
             x1.zero_fill[1] = job->acc_ref;
@@ -68,6 +69,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
             PARESIS_CUDA(cudaMemsetAsync(job->dy_pad, 0, sizeof(float) * np, s));
         }
         paresis_refract_extras x3{};
+        x3.throughput = job->throughput;
         x3.intensity_scale = en.intensity_propag;
         const int rc = paresis_refract_layers_ex(nullptr, en.intensity_propag, en.propag, en.n_propag, job->acc_propag, nullptr,
                                                  want_d ? job->dx_pad : nullptr, want_d ? job->dy_pad : nullptr, job->nx, job->ny,
@@ -121,6 +123,7 @@ extern "C" int paresis_rt_run(const paresis_rt_job* job, paresis_stream stream) 
             // object -> detector: sample beam and reference beam in one pass over I_bs (:469-474), which is
             // cleared behind the pass; the reference beam is summed on the way (:485-486)
             paresis_refract_extras x2{};
+            x2.throughput = job->throughput;
             x2.clear_input = 1;
             x2.sum_ref = job->means ? job->means + e : nullptr;
             x2.intensity_scale = en.intensity_membrane;
@@ -387,6 +390,7 @@ extern "C" int paresis_rt_run_positions(const paresis_rt_job* job, const paresis
         j.probe_start = pos.probe_start; j.probe_end = pos.probe_end;
         if (!pos.probe_start || !pos.probe_end) j.probe = 0;
         j.dx_pad = j.dy_pad = nullptr;
+        if (n_positions > 1) j.throughput = 1;        // launches of neighbouring positions overlap: least work per pixel wins
         rc = paresis_rt_run(&j, slot.stream);
         if (rc) return rc;
         slot.i_bs_dirty = 0;

@@ -28,7 +28,8 @@ struct RefractArgs {
     bool clear_input;
     double* sum_ref;
     double* zero_scalar;
-    float intensity_scale;   // > 0: nominal beam intensity, enables the fixed-point tile kernel (refract_tile.cuh)
+    float intensity_scale;   // > 0: nominal beam intensity, enables the fixed-point tile kernels
+    bool full_tiles;         // tile hops: blocks of the full tile height instead of the wave-filling row count
 };
 
 // The tile hop for several membrane positions in one launch (blockIdx.z): what differs between the positions.
@@ -61,6 +62,7 @@ __device__ __forceinline__ void clean(float& v, float& dx, float& dy, float cx, 
 int dispatch_refract_lean(int n_layers, const RefractArgs<float>& a, cudaStream_t s);
 // ... for n_batch positions at once: a.z[0 .. n_batch) hold their images, the RefractArgs part the shared coefficients
 // (its own map / image pointers are ignored, only out_ref != nullptr and I_in != nullptr select the kernel shape).
+extern int g_lean_rows_override;      // paresis_set_tuning(3, rows): rows per block of the tile hops, 0 = pick_tile_rows
 int dispatch_refract_lean_batch(int n_layers, const LeanArgs& a, int n_batch, cudaStream_t s);
 
 // Stand-alone splat through fixed-point shared-memory tiles (splat_tile.cu): variant 3 of paresis_splat.

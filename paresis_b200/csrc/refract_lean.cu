@@ -7,8 +7,8 @@ namespace paresis {
 template <int NM>
 static int dispatch_lean_shape(const LeanArgs& a, int n_batch, cudaStream_t s) {
     const bool dual = a.z[0].out_ref != nullptr, has_i = a.z[0].I_in != nullptr;
-    if (dual) return has_i ? launch_refract_lean<NM, true, true, 16>(a, n_batch, s) : launch_refract_lean<NM, true, false, 16>(a, n_batch, s);
-    return has_i ? launch_refract_lean<NM, false, true, 16>(a, n_batch, s) : launch_refract_lean<NM, false, false, 16>(a, n_batch, s);
+    if (dual) return has_i ? launch_refract_lean<NM, true, true, LEAN_TR_DUAL>(a, n_batch, s) : launch_refract_lean<NM, true, false, LEAN_TR_DUAL>(a, n_batch, s);
+    return has_i ? launch_refract_lean<NM, false, true, LEAN_TR_SINGLE>(a, n_batch, s) : launch_refract_lean<NM, false, false, LEAN_TR_SINGLE>(a, n_batch, s);
 }
 
 int dispatch_refract_lean_batch(int n_layers, const LeanArgs& a, int n_batch, cudaStream_t s) {

@@ -88,8 +88,20 @@ __device__ __forceinline__ void flush_rows_fast(const unsigned* tile, float* out
     }
 }
 
-#ifndef LEAN_MIN_BLOCKS
-#define LEAN_MIN_BLOCKS(DUAL, NM) ((DUAL) ? 4 : 6)
+// resident blocks per SM the kernels are compiled for (register cap = 65536 / (256 * blocks)); -D overrides for A/B builds
+#ifndef LEAN_MIN_BLOCKS_DUAL
+#define LEAN_MIN_BLOCKS_DUAL 3      // 80 registers: no spills in the row loop; same-box A/B: +4.7 % on the job over 4 blocks x 64
+#endif
+#ifndef LEAN_MIN_BLOCKS_SINGLE
+#define LEAN_MIN_BLOCKS_SINGLE 6
+#endif
+#define LEAN_MIN_BLOCKS(DUAL, NM) ((DUAL) ? LEAN_MIN_BLOCKS_DUAL : LEAN_MIN_BLOCKS_SINGLE)
+// source rows a tile is built for (two-beam / one-beam kernels)
+#ifndef LEAN_TR_DUAL
+#define LEAN_TR_DUAL 16
+#endif
+#ifndef LEAN_TR_SINGLE
+#define LEAN_TR_SINGLE 16
 #endif
 constexpr unsigned MISS_REF = 0x40000000u, MISS_TWIN = 0x80000000u;
 
@@ -101,7 +113,9 @@ refract_lean_kernel(const LeanArgs a) {
     const LeanItem& it = a.z[ZB ? blockIdx.z : 0];
     constexpr int H = 4;
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H, NT = DUAL ? 2 : 1;
-    static_assert(((1ull << 32) / (TR * TILE_COLS)) >= (2ull << FIX_BITS), "rays up to 2 x intensity_scale must fit the fixed-point tile");
+    // a cell can receive every ray of the block: rays are admitted to the tile up to 2^32 / (TR * 256) units each (vmax_bits
+    // below), brighter ones take the fp32 list.  TR = 16 admits 2 x intensity_scale, TR = 24 still 1.33 x.
+    static_assert(((1ull << 32) / (TR * TILE_COLS)) >= (5ull << (FIX_BITS - 2)), "rays up to 1.25 x intensity_scale must fit the fixed-point tile");
     extern __shared__ __align__(16) unsigned tile_smem[];
     uint4* const queue = reinterpret_cast<uint4*>(tile_smem + NT * SR * SC);
     unsigned* const qcount = tile_smem + NT * SR * SC + 4 * MQ;
@@ -388,7 +402,9 @@ static int launch_refract_lean(const LeanArgs& a_in, int n_batch, cudaStream_t s
     }
     LeanArgs a = a_in;
     const int strips = div_up(a.f.ny, TILE_COLS);
-    a.rows = pick_tile_rows(a.f.nx, strips * n_batch, slots_of[dev], TR);
+    // rows per block: the wave-filling count for a launch that runs alone, the whole tile when launches overlap anyway
+    a.rows = g_lean_rows_override > 0 ? (g_lean_rows_override < TR ? g_lean_rows_override : TR)
+                                      : (a.full_tiles ? TR : pick_tile_rows(a.f.nx, strips * n_batch, slots_of[dev], TR));
     dim3 grid(strips, div_up(a.f.nx, a.rows), n_batch);
     if (n_batch > 1) refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, true><<<grid, TILE_COLS, smem, s>>>(a);
     else refract_lean_kernel<NM, DUAL, HAS_I, TR, MQ, false><<<grid, TILE_COLS, smem, s>>>(a);

@@ -207,6 +207,7 @@ static int g_rows_override = 0;
 // paresis_refract_extras.intensity_scale), -1 = one column per thread straight to L2 (this file; what runs for everything
 // else: displacement output, phase input, callers that give no intensity scale)
 static int g_tile_config = 0;
+int g_lean_rows_override = 0;      // paresis_set_tuning(3, rows)
 
 // rows per warp: enough blocks for ~2 waves of 148 SMs x 8 resident blocks, few halo re-reads
 static int pick_rows(int nx, int ny) {
@@ -257,6 +258,7 @@ extern "C" int paresis_set_tuning(int key, int value) {
         case 0: g_fused_mode = value == 0 ? 0 : 2; return PARESIS_OK;
         case 1: g_rows_override = value; return PARESIS_OK;
         case 2: g_tile_config = value < 0 ? -1 : 0; return PARESIS_OK;
+        case 3: paresis::g_lean_rows_override = value > 0 ? value : 0; return PARESIS_OK;
         default: set_last_error("paresis_set_tuning: unknown key %d", key); return PARESIS_ERR_ARG;
     }
 }
@@ -378,6 +380,7 @@ extern "C" int paresis_refract_layers_ex(const float* intensity_in, float intens
         a.sum_ref = out_ref ? extras->sum_ref : nullptr;
         a.zero_scalar = extras->zero_scalar;
         a.intensity_scale = extras->intensity_scale > 0.f && extras->intensity_scale < 3.0e38f ? extras->intensity_scale : 0.f;
+        a.full_tiles = extras->throughput != 0;
     }
     switch (n_layers) {
         case 1: return dispatch_layers<1>(a, s);
