@@ -96,6 +96,11 @@ __device__ __forceinline__ void flush_rows_fast(const unsigned* tile, float* out
 #define LEAN_MIN_BLOCKS_SINGLE 6
 #endif
 #define LEAN_MIN_BLOCKS(DUAL, NM) ((DUAL) ? LEAN_MIN_BLOCKS_DUAL : LEAN_MIN_BLOCKS_SINGLE)
+// pixels a ray may move and still take the tile (the tile carries a halo of this many cells on every side); a multiple
+// of 4 (vector flush), and 8 no longer leaves room for three blocks of the two-beam kernel: 4 is the only useful value
+#ifndef LEAN_REACH
+#define LEAN_REACH 4
+#endif
 // source rows a tile is built for (two-beam / one-beam kernels)
 #ifndef LEAN_TR_DUAL
 #define LEAN_TR_DUAL 16
@@ -111,7 +116,8 @@ refract_lean_kernel(const LeanArgs a) {
     // this block's membrane position; a single-position launch (ZB = false) addresses its pointers as plain kernel
     // parameters instead of through a register-indexed constant load per use
     const LeanItem& it = a.z[ZB ? blockIdx.z : 0];
-    constexpr int H = 4;
+    constexpr int H = LEAN_REACH;
+    static_assert(H % 4 == 0, "the fast flush issues 128-bit REDs at column block * 256 - H: the reach must keep them aligned");
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H, NT = DUAL ? 2 : 1;
     // a cell can receive every ray of the block: rays are admitted to the tile up to 2^32 / (TR * 256) units each (vmax_bits
     // below), brighter ones take the fp32 list.  TR = 16 admits 2 x intensity_scale, TR = 24 still 1.33 x.
@@ -385,7 +391,7 @@ refract_lean_kernel(const LeanArgs a) {
 
 template <int NM, bool DUAL, bool HAS_I, int TR>
 static int launch_refract_lean(const LeanArgs& a_in, int n_batch, cudaStream_t s) {
-    constexpr int H = 4, MQ = 256;   // 4 resident blocks of the two-beam hop: 2 tiles + list <= 56 KB
+    constexpr int H = LEAN_REACH, MQ = 256;   // two tiles + list of the two-beam hop: 58 KB
     constexpr int SR = TR + 2 * H + 1, SC = TILE_COLS + 2 * H;
     constexpr size_t smem = sizeof(unsigned) * (SR * SC * (DUAL ? 2 : 1) + 4 * MQ + 4);
     static int slots_of[32] = {0};   // resident blocks x SMs, per device (the attribute and the occupancy are per device)
